@@ -1,0 +1,127 @@
+"""ctypes binding of the CPU oracle (oracle/rayn_oracle.cpp).  TEST INFRASTRUCTURE ONLY.
+
+Importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs.  Nothing under rayn_b200/ may import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from rayn_b200 import _lib as L
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_build", "librayn_oracle.so")
+fp = C.POINTER(C.c_float)
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(HERE, "rayn_oracle.cpp")
+    deps = [src, os.path.join(HERE, "..", "include", "rayn_b200.h"), os.path.join(HERE, "..", "rayn_b200", "csrc", "detmath.h")]
+    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps):
+        subprocess.run(["make", "-C", HERE, "-B"], check=True, capture_output=True)
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        l = C.CDLL(LIB_PATH)
+        l.rayn_oracle_selfcheck.restype = C.c_int32
+        l.rayn_oracle_render_frame.restype = C.c_int32
+        l.rayn_oracle_render_frame.argtypes = [C.POINTER(L.RaynSceneDesc), C.POINTER(L.RaynFrameDesc), C.POINTER(L.RaynFilmPlanes),
+                                               C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int64),
+                                               C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        l.rayn_oracle_kat_detmath.argtypes = [C.c_int32, C.c_int64, fp, fp, fp]
+        l.rayn_oracle_kat_sdf_dist.argtypes = [C.POINTER(L.RaynHitable), C.c_int64, fp, fp]
+        l.rayn_oracle_kat_sdf_hit.argtypes = [C.POINTER(L.RaynHitable), C.POINTER(L.RaynRenderConsts), C.c_int64, fp, fp, fp,
+                                              C.c_float, C.c_int32, fp]
+        l.rayn_oracle_kat_occluded.argtypes = [C.POINTER(L.RaynSceneDesc), C.c_int64, fp, fp, fp]
+        l.rayn_oracle_kat_closest_hit.argtypes = [C.POINTER(L.RaynSceneDesc), C.c_int32, C.c_int64, fp, fp, fp, C.POINTER(C.c_int32)]
+        if l.rayn_oracle_selfcheck() != 0:
+            raise RuntimeError("oracle was built with FP contraction on: rebuild with -ffp-contract=off")
+        _lib = l
+    return _lib
+
+
+def _f(a):
+    return a.ctypes.data_as(fp)
+
+
+def render(world, camera, inputs, tile_size, integrator, time_range, n_threads=0, subsample_k=1, tile_offset=0, tile_stride=1,
+           queue_log=False):
+    """CPU render of the same FrameInputs.  Returns (planes dict, info dict)."""
+    from rayn_b200.film import make_frame_desc
+    desc, keep = world.flatten(camera)
+    w, h = inputs.width, inputs.height
+    planes = {"color": np.zeros(3 * w * h, np.float32), "alpha": np.zeros(w * h, np.float32),
+              "background": np.zeros(3 * w * h, np.float32), "normal": np.zeros(3 * w * h, np.float32)}
+    p = L.RaynFilmPlanes(planes["color"].ctypes.data, planes["alpha"].ctypes.data, planes["background"].ctypes.data,
+                         planes["normal"].ctypes.data, L.MEM_HOST)
+    ptrs = tuple(a.ctypes.data for a in inputs.arrays())
+    f = make_frame_desc(w, h, tile_size, inputs.samples, integrator, inputs.frame, time_range, ptrs, L.MEM_HOST, tile_offset,
+                        tile_stride, (inputs.sets_1d, inputs.sets_2d))
+    qbuf, qcap = None, 0
+    if queue_log:
+        qcap = 64 + 8 * (w * h * inputs.spp + 64 * 64) * (integrator.max_bounces + 1)
+        qbuf = np.empty(qcap, np.int32)
+    qn = C.c_int64(0)
+    counters = (C.c_int64 * 4)()
+    tiles = C.c_int64(0)
+    rc = lib().rayn_oracle_render_frame(C.byref(desc), C.byref(f), C.byref(p), n_threads, subsample_k,
+                                        qbuf.ctypes.data_as(C.POINTER(C.c_int32)) if queue_log else None, qcap, C.byref(qn),
+                                        counters, C.byref(tiles))
+    if rc != 0:
+        raise RuntimeError(f"oracle render failed: {rc}")
+    info = {"extend_rays": counters[0], "shade_lanes": counters[1], "shadow_rays": counters[2], "sdf_evals_extend": counters[3],
+            "tiles": tiles.value}
+    if queue_log:
+        if qn.value > qcap:
+            raise RuntimeError("oracle queue log overflow")
+        info["queue_log"] = qbuf[:qn.value].copy()
+    return planes, info
+
+
+def kat_detmath(op, a, b=None):
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b if b is not None else a, np.float32)
+    out = np.empty_like(a)
+    lib().rayn_oracle_kat_detmath(op, a.size, _f(a), _f(b), _f(out))
+    return out
+
+
+def kat_sdf_dist(hitable, points):
+    p = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+    out = np.empty(len(p), np.float32)
+    lib().rayn_oracle_kat_sdf_dist(C.byref(hitable), len(p), _f(p), _f(out))
+    return out
+
+
+def kat_sdf_hit(hitable, consts, origins, dirs, t_max, thr_scale, thr_const=0):
+    o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+    d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+    tm = np.ascontiguousarray(t_max, np.float32)
+    out = np.empty(len(o), np.float32)
+    lib().rayn_oracle_kat_sdf_hit(C.byref(hitable), C.byref(consts), len(o), _f(o), _f(d), _f(tm), thr_scale, thr_const, _f(out))
+    return out
+
+
+def kat_occluded(scene_desc, start, end):
+    s = np.ascontiguousarray(start, np.float32).reshape(-1, 3)
+    e = np.ascontiguousarray(end, np.float32).reshape(-1, 3)
+    out = np.empty(len(s), np.float32)
+    lib().rayn_oracle_kat_occluded(C.byref(scene_desc), len(s), _f(s), _f(e), _f(out))
+    return out
+
+
+def kat_closest_hit(scene_desc, depth, origins, dirs):
+    o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+    d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+    t = np.empty(len(o), np.float32)
+    obj = np.empty(len(o), np.int32)
+    lib().rayn_oracle_kat_closest_hit(C.byref(scene_desc), depth, len(o), _f(o), _f(d), _f(t), obj.ctypes.data_as(C.POINTER(C.c_int32)))
+    return t, obj

@@ -1,0 +1,597 @@
+// rt_kernels.cuh — the wavefront kernels (sm_100a) and their launch-time data layout.
+//
+// Data layout in HBM (one "pass" = a batch of 16x16 film tiles):
+//   per path (never moves; a path's id encodes pixel and sample):
+//     o_time[g]  float4  origin.xyz, time            (ray.rs:8-9)
+//     d_t[g]     float4  dir.xyz, closest-hit t      (ray.rs:10, hitable.rs:52-55)
+//     rad[g]     float4  radiance.xyz, -             (ray.rs:11)
+//     thr[g]     float4  throughput.xyz, -           (ray.rs:12)
+//     nrm0[g]    float4  depth-0 world normal.xyz, bits(slot0+1) (integrator.rs:161-169)
+//     term[g]    u32     kind<<30 | depth<<20 | slot at termination (integrator.rs:178-203)
+//   per tile, index queues (the "ray queue": what is compacted and partitioned is a 4-byte id):
+//     q_live[ts*R + i]    live path ids in packet order           (film.rs:608-625)
+//     q_key[ts*R + i]     object hit by q_live[i], -1 = nothing   (hitable.rs:203-209)
+//     q_shade[ts*QS + s]  shading slots: per-object bins, each padded to x4 with -1
+//                         (hitable.rs:94-133)
+//   g = ts*R + id, id = (xl*th + yl)*spp + sample  — the reference's raygen order
+//   `for x { for y { for samp { 4 lanes } } }` (film.rs:456-464).
+#pragma once
+#include "rt_device.cuh"
+
+namespace rt {
+
+struct DevFrame {
+  int W, H, tile_w, tile_h, samples, spp, max_bounces, vm;
+  int ntx, nty, sets_1d, sets_2d;
+  float t0, t1;
+  const float* __restrict__ s1;   // [spp*sets_1d]
+  const float* __restrict__ s2;   // [2*spp*sets_2d]
+  const float* __restrict__ scramble;  // [W*H]
+  const float* __restrict__ fis;  // [512]
+};
+
+struct PassBufs {
+  int n_tiles;  // tiles in this pass
+  int R;        // path slots per tile = tile_w*tile_h*spp
+  int QS;       // shading-queue stride per tile = R + 4*n_hit
+  const int* __restrict__ tile_ids;  // [n_tiles] global tile index
+  float4* o_time;
+  float4* d_t;
+  float4* rad;
+  float4* thr;
+  float4* nrm0;
+  uint32_t* term;
+  int* q_live;
+  int* q_key;
+  int* q_shade;
+  int* n_live;     // [n_tiles]
+  int* n_slots;    // [n_tiles]
+  int* bin_start;  // [n_tiles*(RAYN_MAX_HITABLES+1)]
+  unsigned long long* counters;  // [8] stats
+};
+
+enum { CNT_EXTEND_RAYS = 0, CNT_SHADE_LANES = 1, CNT_SHADOW_RAYS = 2, CNT_EVALS_EXTEND = 3, CNT_EVALS_SHADOW = 4 };
+
+#define TERM_NONE 0u
+#define TERM_COLOR 1u
+#define TERM_BACKGROUND 2u
+
+struct TileGeom {
+  int x0, y0, tw, th, npaths;
+};
+RT_D TileGeom tile_geom(const DevFrame& fr, int tile_id) {
+  TileGeom g;
+  int tx = tile_id / fr.nty, ty = tile_id % fr.nty;  // film.rs:403-405: x-major
+  g.x0 = tx * fr.tile_w;
+  g.y0 = ty * fr.tile_h;
+  int x1 = min(g.x0 + fr.tile_w, fr.W), y1 = min(g.y0 + fr.tile_h, fr.H);  // film.rs:406-409
+  g.tw = x1 - g.x0;
+  g.th = y1 - g.y0;
+  g.npaths = g.tw * g.th * fr.spp;
+  return g;
+}
+
+// Samples::sample_1d / sample_2d, sampler.rs:62-64,92-94
+RT_D float samp1(const DevFrame& fr, int sample, float scramble, int set) {
+  return dm::fract(__ldg(fr.s1 + sample + (size_t)fr.spp * set) + scramble);
+}
+RT_D float samp2(const DevFrame& fr, int dim, int sample, float scramble, int set) {
+  return dm::fract(__ldg(fr.s2 + dim + (size_t)sample * 2 + (size_t)fr.spp * 2 * set) + scramble);
+}
+
+RT_D void warp_add(unsigned long long* ctr, int v) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(ctr, (unsigned long long)v);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1 raygen: film.rs:456-529 + sample_uv :695-709 + camera.rs get_rays
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ DevScene sc, const DevFrame fr, const PassBufs pb) {
+  const int ts = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const TileGeom tg = tile_geom(fr, pb.tile_ids[ts]);
+  if (i == 0) pb.n_live[ts] = tg.npaths;
+  if (i >= tg.npaths) return;
+  const int pl = i / fr.spp, s = i - pl * fr.spp;
+  const int xl = pl / tg.th, yl = pl - xl * tg.th;
+  const int x = tg.x0 + xl, y = tg.y0 + yl;
+  const float scramble = __ldg(fr.scramble + x + (size_t)y * fr.W);
+  const float fx = fis_sample(fr.fis, samp2(fr, 0, s, scramble, 0));
+  const float fy = fis_sample(fr.fis, samp2(fr, 1, s, scramble, 0));
+  const float sx = ((float)x + 0.5f) + fx;
+  const float sy = ((float)y + 0.5f) + fy;
+  const float u = (1.0f / (float)fr.W) * sx;
+  const float v = (1.0f / (float)fr.H) * sy;
+  const float time = fr.t0 + (fr.t1 - fr.t0) * samp1(fr, s, scramble, 0);
+  const float ls0 = samp2(fr, 0, s, scramble, 1), ls1 = samp2(fr, 1, s, scramble, 1);
+  f3 ro, rd;
+  camera_ray(sc.cam, u, v, ls0, ls1, &ro, &rd);
+  const size_t g = (size_t)ts * pb.R + i;
+  pb.o_time[g] = make_float4(ro.x, ro.y, ro.z, time);
+  pb.d_t[g] = make_float4(rd.x, rd.y, rd.z, 0.0f);
+  pb.rad[g] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  pb.thr[g] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+  pb.nrm0[g] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
+  pb.term[g] = 0u;
+  pb.q_live[g] = i;
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 extend: HitableStore::add_hits (hitable.rs:170-210) incl. the sphere-march
+// (sdf.rs:59-83).  One thread per live ray: reads float4 o_time + float4 d, writes t + key.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_extend(const __grid_constant__ DevScene sc, const PassBufs pb, const Thr thr) {
+  const int ts = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = pb.n_live[ts];
+  if ((i & ~31) >= n) return;
+  int evals = 0;
+  const bool act = i < n;
+  if (act) {
+    const size_t q = (size_t)ts * pb.R + i;
+    const int id = pb.q_live[q];
+    const size_t g = (size_t)ts * pb.R + id;
+    const float4 o4 = pb.o_time[g];
+    const float4 d4 = pb.d_t[g];
+    float t;
+    int obj;
+    closest_hit(sc, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z), thr, &t, &obj, &evals);
+    pb.d_t[g].w = t;
+    pb.q_key[q] = obj;
+  }
+  warp_add(pb.counters + CNT_EXTEND_RAYS, act ? 1 : 0);
+  warp_add(pb.counters + CNT_EVALS_EXTEND, evals);
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 bin+pad: HitStore::add_hit / process_hits (hitable.rs:90-133).  Stable partition of a
+// tile's live rays by object id, every bin padded to a multiple of 4 with -1.  One CTA per
+// tile; chunks of BIN_T rays; per-warp __match_any_sync ranks + cross-warp offsets in smem.
+// ------------------------------------------------------------------------------------------
+#define BIN_T 256
+__global__ void __launch_bounds__(BIN_T) k_bin(const PassBufs pb, const int n_hit) {
+  const int ts = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = pb.n_live[ts];
+  __shared__ int cnt[RAYN_MAX_HITABLES];
+  __shared__ int start[RAYN_MAX_HITABLES + 1];
+  __shared__ int running[RAYN_MAX_HITABLES];
+  __shared__ int wcnt[BIN_T / 32][RAYN_MAX_HITABLES];
+  const int* __restrict__ qk = pb.q_key + (size_t)ts * pb.R;
+  const int* __restrict__ ql = pb.q_live + (size_t)ts * pb.R;
+  int* __restrict__ qs = pb.q_shade + (size_t)ts * pb.QS;
+  if (tid < RAYN_MAX_HITABLES) cnt[tid] = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += BIN_T) {
+    const int i = base + tid;
+    const int key = i < n ? qk[i] : -1;
+    const unsigned m = __match_any_sync(0xffffffffu, key);
+    if (key >= 0 && (m & ((1u << lane) - 1)) == 0) atomicAdd(&cnt[key], __popc(m));
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int off = 0;
+    for (int o = 0; o < n_hit; ++o) {
+      start[o] = off;
+      running[o] = off;
+      off += (cnt[o] + 3) & ~3;
+    }
+    start[n_hit] = off;
+    pb.n_slots[ts] = off;
+  }
+  __syncthreads();
+  if (tid <= n_hit) pb.bin_start[ts * (RAYN_MAX_HITABLES + 1) + tid] = start[tid];
+  for (int base = 0; base < n; base += BIN_T) {
+    const int i = base + tid;
+    const int key = i < n ? qk[i] : -1;
+    const int id = i < n ? ql[i] : -1;
+    for (int k = tid; k < (BIN_T / 32) * RAYN_MAX_HITABLES; k += BIN_T) (&wcnt[0][0])[k] = 0;
+    __syncthreads();
+    const unsigned m = __match_any_sync(0xffffffffu, key);
+    const int rank = __popc(m & ((1u << lane) - 1));
+    if (key >= 0 && rank == 0) wcnt[warp][key] = __popc(m);
+    __syncthreads();
+    if (key >= 0) {
+      int off = running[key];
+      for (int w = 0; w < warp; ++w) off += wcnt[w][key];
+      qs[off + rank] = id;
+    }
+    __syncthreads();
+    if (tid < n_hit) {
+      int tot = 0;
+      for (int w = 0; w < BIN_T / 32; ++w) tot += wcnt[w][tid];
+      running[tid] += tot;
+    }
+    __syncthreads();
+  }
+  if (tid < n_hit)
+    for (int k = start[tid] + cnt[tid]; k < start[tid + 1]; ++k) qs[k] = -1;  // Ray::new_invalid padding
+}
+
+// ------------------------------------------------------------------------------------------
+// K4 shade (+K5 shadow fused): get_shading_info (sdf.rs:85-101 / sphere.rs:74-86), sample
+// draw (film.rs:564-589), PathTracingIntegrator::integrate (integrator.rs:47-205).
+// One thread per shading slot; lanes 4k..4k+3 of a warp are exactly one reference packet and
+// exchange their light choices with __shfl_sync.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DevScene sc, const DevFrame fr, const PassBufs pb,
+                                               const int depth, const Thr thr) {
+  const int ts = blockIdx.y;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nslots = pb.n_slots[ts];
+  if ((s & ~31) >= nslots) return;  // warp-uniform
+  const int lane = threadIdx.x & 31;
+  int* __restrict__ qs = pb.q_shade + (size_t)ts * pb.QS;
+  const int id = s < nslots ? qs[s] : -1;
+  const bool valid = id >= 0;
+  const TileGeom tg = tile_geom(fr, pb.tile_ids[ts]);
+  // sample index / scramble: padded lanes are Ray::new_invalid -> sample 0, scramble 0 (ray.rs:54-66)
+  int sample = 0;
+  float scramble = 0.0f;
+  int pl = 0;
+  if (valid) {
+    pl = id / fr.spp;
+    sample = id - pl * fr.spp;
+    const int xl = pl / tg.th, yl = pl - xl * tg.th;
+    scramble = __ldg(fr.scramble + (tg.x0 + xl) + (size_t)(tg.y0 + yl) * fr.W);
+  }
+  const int n1 = 3 + fr.vm, n2h = (12 + 8 * fr.vm) / 2;  // 1-D sets / 2-D sets per depth
+  const int set1 = 1 + depth * n1, set2 = 2 + depth * n2h;
+  const int nl = sc.n_lights;
+  // light choices: one index per lane per light-selection sample (integrator.rs:76-77,100-102)
+  unsigned pack = 0;
+  if (nl > 0) {
+    pack = (unsigned)light_index(samp1(fr, sample, scramble, set1 + 0), nl) |
+           ((unsigned)light_index(samp1(fr, sample, scramble, set1 + 1), nl) << 8) |
+           ((unsigned)light_index(samp1(fr, sample, scramble, set1 + 2), nl) << 16);
+  }
+  unsigned packs[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) packs[k] = __shfl_sync(0xffffffffu, pack, (lane & ~3) + k);
+  warp_add(pb.counters + CNT_SHADE_LANES, valid ? 1 : 0);
+  int evals = 0, shadows = 0;
+  if (valid) {
+    // object of this slot from the tile's bin table
+    const int* __restrict__ bs = pb.bin_start + ts * (RAYN_MAX_HITABLES + 1);
+    int obj = 0;
+    while (obj + 1 < sc.n_hit && s >= bs[obj + 1]) ++obj;
+    const RaynHitable& h = sc.hit[obj];
+    const RaynMaterial& mat = sc.mat[h.material];
+    const size_t g = (size_t)ts * pb.R + id;
+    const float4 o4 = pb.o_time[g], d4 = pb.d_t[g], r4 = pb.rad[g], t4 = pb.thr[g];
+    ShadingPoint sp;
+    sp.o = mk3(o4.x, o4.y, o4.z);
+    sp.d = mk3(d4.x, d4.y, d4.z);
+    sp.time = o4.w;
+    sp.t = d4.w;
+    shading_info(sc, h, thr, sp, &evals);
+    f3 radiance = mk3(r4.x, r4.y, r4.z), throughput = mk3(t4.x, t4.y, t4.z);
+    const f3 wo = -sp.d;
+    const bool has_ext = sc.vol.has_extinction != 0;
+    const float neg_rho_t = -sc.vol.coeff_extinction;
+    const float vt = has_ext ? dm::exp(neg_rho_t * sp.t) : 1.0f;  // integrator.rs:64-68
+    radiance = radiance + bsdf_le(mat, wo) * throughput * vt;        // :70-71
+    const bool recv = receives_light(mat);
+
+    if (recv && nl > 0) {  // :73-94
+      const float correction = (float)nl / 4.0f;
+#pragma unroll 1
+      for (int i = 0; i < 4; ++i) {
+        const int li_idx = (int)(packs[i] & 0xffu);
+        const float u0 = samp2(fr, 0, sample, scramble, set2 + i), u1 = samp2(fr, 1, sample, scramble, set2 + i);
+        // surface_sample_one_light :207-240
+        f3 end_point, li;
+        float pdf;
+        light_sample(sc.light[li_idx], u0, u1, sp.point, &end_point, &li, &pdf);
+        f3 wi = end_point - sp.point;
+        const float dist = mag(wi);
+        wi = wi / dist;
+        const f3 occlude_point = sp.point + sp.normal * dm::signum(dot(sp.normal, wi)) * sp.offset_by;
+        const float occluded = test_occluded(sc, occlude_point, end_point, &evals);
+        ++shadows;
+        const f3 f = bsdf_f(mat, wo, wi, sp.normal) * dm::max(dot(sp.normal, wi), 0.0f);
+        const float transmission = has_ext ? dm::exp(neg_rho_t * dist) : 1.0f;
+        const f3 contrib = li * f * transmission * occluded / pdf;
+        radiance = radiance + contrib * throughput * correction * vt;
+      }
+    }
+    if (sc.vol.has_scattering && nl > 0) {  // :96-132
+      const float rho_s = sc.vol.coeff_scattering;
+      const float correction = (float)nl / 4.0f / (float)fr.vm;
+      const float vol_sample = samp1(fr, sample, scramble, set1 + 1);  // samples_1d[1], :115
+#pragma unroll 1
+      for (int march = 0; march < fr.vm; ++march) {
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+          const int li_idx = (int)((packs[i] >> (8 * (march + 1))) & 0xffu);
+          const int set = set2 + 4 + 4 * march + i;  // samples_2d[8 + 8*march + 2i]
+          const float u0 = samp2(fr, 0, sample, scramble, set), u1 = samp2(fr, 1, sample, scramble, set);
+          // volume_sample_one_light :242-281
+          const RaynLight& L = sc.light[li_idx];
+          float vol_dist, vol_pdf;
+          light_sample_volume(L, vol_sample, sp.o, sp.d, sp.t, &vol_dist, &vol_pdf);
+          const f3 sampled_point = sp.o + sp.d * vol_dist;
+          f3 end_point, li;
+          float light_pdf;
+          light_sample(L, u0, u1, sampled_point, &end_point, &li, &light_pdf);
+          const f3 wi = end_point - sampled_point;
+          const float dist_point_to_light = mag(wi);
+          const float occluded = test_occluded(sc, sampled_point, end_point, &evals);
+          ++shadows;
+          const float f = 1.0f / (4.0f * RT_PI);
+          const float tr_light = has_ext ? dm::exp(neg_rho_t * dist_point_to_light) : 1.0f;
+          const f3 contrib = li * f * tr_light * occluded / (vol_pdf * light_pdf);
+          const float transmission = has_ext ? dm::exp(neg_rho_t * vol_dist) : 1.0f;
+          radiance = radiance + contrib * throughput * correction * rho_s * transmission;
+        }
+      }
+    }
+
+    if (recv) {  // :134-188
+      const int setb = set2 + 4 + 4 * fr.vm;  // samples_2d[8 + 8*vm ..]
+      const Scatter se = bsdf_scatter(mat, wo, sp, samp1(fr, sample, scramble, set1 + 3), samp2(fr, 0, sample, scramble, setb),
+                                      samp2(fr, 1, sample, scramble, setb), samp2(fr, 0, sample, scramble, setb + 1),
+                                      samp2(fr, 1, sample, scramble, setb + 1));
+      const float ndl = dm::abs(dot(se.wi, sp.normal));
+      f3 new_throughput = throughput * vt * se.f * ndl / se.pdf;
+      float roulette_factor = 0.0f;
+      if (depth > 2) {
+        roulette_factor = dm::max(1.0f - component_max(throughput), 0.05f);
+        new_throughput = new_throughput / (1.0f - roulette_factor);
+      }
+      if (depth == 0)  // Alpha(1) + WorldNormal(n), :161-169
+        pb.nrm0[g] = make_float4(sp.normal.x, sp.normal.y, sp.normal.z, __uint_as_float((unsigned)s + 1u));
+      const float roulette_sample = samp1(fr, sample, scramble, set1 + 4);
+      if (depth >= fr.max_bounces || roulette_sample < roulette_factor) {
+        pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+        pb.term[g] = (TERM_COLOR << 30) | ((unsigned)depth << 20) | (unsigned)s;
+        qs[s] = -1;
+      } else {
+        // WShadingPoint::create_rays, hitable.rs:42-47
+        const f3 no = sp.point + sp.normal * dm::signum(dot(sp.normal, se.wi)) * sp.offset_by;
+        if (!any_nan(new_throughput)) throughput = new_throughput;  // :181-183
+        pb.o_time[g] = make_float4(no.x, no.y, no.z, sp.time);
+        pb.d_t[g] = make_float4(se.wi.x, se.wi.y, se.wi.z, 0.0f);
+        pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+        pb.thr[g] = make_float4(throughput.x, throughput.y, throughput.z, 0.0f);
+      }
+    } else {  // :189-203
+      pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+      pb.term[g] = ((depth == 0 ? TERM_BACKGROUND : TERM_COLOR) << 30) | ((unsigned)depth << 20) | (unsigned)s;
+      qs[s] = -1;
+    }
+  }
+  warp_add(pb.counters + CNT_EVALS_SHADOW, evals);
+  warp_add(pb.counters + CNT_SHADOW_RAYS, shadows);
+}
+
+// ------------------------------------------------------------------------------------------
+// K6 compact: film.rs:604-625.  Order-preserving stream compaction of the surviving slots of
+// a tile into the next live queue: per-warp __ballot_sync + popc prefix, cross-warp offsets
+// in shared memory, running tile offset.  (Padding the survivors to x4, film.rs:608-610, has
+// no observable effect: add_hits drops invalid lanes, hitable.rs:204.)
+// ------------------------------------------------------------------------------------------
+#define CMP_T 256
+__global__ void __launch_bounds__(CMP_T) k_compact(const PassBufs pb) {
+  const int ts = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = pb.n_slots[ts];
+  const int* __restrict__ qs = pb.q_shade + (size_t)ts * pb.QS;
+  int* __restrict__ ql = pb.q_live + (size_t)ts * pb.R;
+  __shared__ int wtot[CMP_T / 32];
+  __shared__ int running;
+  if (tid == 0) running = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += CMP_T) {
+    const int i = base + tid;
+    const int id = i < n ? qs[i] : -1;
+    const unsigned b = __ballot_sync(0xffffffffu, id >= 0);
+    const int rank = __popc(b & ((1u << lane) - 1));
+    if (lane == 0) wtot[warp] = __popc(b);
+    __syncthreads();
+    int off = running;
+    for (int w = 0; w < warp; ++w) off += wtot[w];
+    if (id >= 0) ql[off + rank] = id;
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < CMP_T / 32; ++w) tot += wtot[w];
+      running += tot;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) pb.n_live[ts] = running;
+}
+
+// ------------------------------------------------------------------------------------------
+// K7 film resolve: Tile::add_sample (film.rs:167-172, :54-61) + copy_from_tile (:82-98).
+// The reference adds a pixel's samples in wavefront order: by depth, then by shading-slot
+// order inside the tile.  Each path recorded (depth, slot) when it terminated, so one CTA per
+// pixel sorts its spp paths by that key (bitonic, shared memory) and sums them sequentially
+// in exactly that order -> bit-identical film, no float atomics, deterministic across runs
+// and GPU counts.  Then / spp.
+// ------------------------------------------------------------------------------------------
+#define RES_T 128
+RT_D void bitonic_sort(uint32_t* key, int* val, int np) {
+  for (int k = 2; k <= np; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < np; i += RES_T) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const bool up = (i & k) == 0;
+          const uint32_t a = key[i], b = key[ixj];
+          if ((a > b) == up) {
+            key[i] = b;
+            key[ixj] = a;
+            const int t = val[i];
+            val[i] = val[ixj];
+            val[ixj] = t;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(RES_T) k_resolve(const DevFrame fr, const PassBufs pb, float* __restrict__ color,
+                                                   float* __restrict__ alpha, float* __restrict__ background,
+                                                   float* __restrict__ normal, const int np) {
+  extern __shared__ unsigned char smem_raw[];
+  uint32_t* key = reinterpret_cast<uint32_t*>(smem_raw);
+  int* val = reinterpret_cast<int*>(smem_raw) + np;
+  __shared__ int n_sorted;
+  const int ts = blockIdx.y, pl = blockIdx.x, tid = threadIdx.x;
+  const TileGeom tg = tile_geom(fr, pb.tile_ids[ts]);
+  if (pl >= tg.tw * tg.th) return;
+  const int xl = pl / tg.th, yl = pl - xl * tg.th;
+  const size_t pix = (size_t)(tg.x0 + xl) + (size_t)(tg.y0 + yl) * fr.W;
+  const size_t g0 = (size_t)ts * pb.R + (size_t)pl * fr.spp;
+  const float div = (float)fr.spp;
+
+  // ---- sort A: depth-0 receives_light hits by slot0 -> WorldNormal, Alpha
+  for (int i = tid; i < np; i += RES_T) {
+    uint32_t k = 0xffffffffu;
+    if (i < fr.spp) {
+      const uint32_t s0 = __float_as_uint(pb.nrm0[g0 + i].w);
+      if (s0) k = s0;
+    }
+    key[i] = k;
+    val[i] = i;
+  }
+  __syncthreads();
+  bitonic_sort(key, val, np);
+  if (tid < 4) {
+    float acc = 0.0f;
+    for (int i = 0; i < np && key[i] != 0xffffffffu; ++i) {
+      const float4 n4 = pb.nrm0[g0 + val[i]];
+      acc += tid == 0 ? n4.x : tid == 1 ? n4.y : tid == 2 ? n4.z : 1.0f;
+    }
+    if (tid < 3)
+      normal[3 * pix + tid] = acc / div;
+    else
+      alpha[pix] = acc / div;
+  }
+  __syncthreads();
+  // ---- sort B: terminated paths by (depth, slot) -> Color / Background
+  for (int i = tid; i < np; i += RES_T) {
+    uint32_t k = 0xffffffffu;
+    if (i < fr.spp) {
+      const uint32_t t = pb.term[g0 + i];
+      if (t >> 30) k = t & 0x3fffffffu;
+    }
+    key[i] = k;
+    val[i] = i;
+  }
+  __syncthreads();
+  bitonic_sort(key, val, np);
+  if (tid < 6) {
+    const int ch = tid % 3;
+    const uint32_t want = tid < 3 ? TERM_COLOR : TERM_BACKGROUND;
+    float acc = 0.0f;
+    for (int i = 0; i < np && key[i] != 0xffffffffu; ++i) {
+      const size_t g = g0 + val[i];
+      if ((pb.term[g] >> 30) == want) {
+        const float4 r4 = pb.rad[g];
+        acc += ch == 0 ? r4.x : ch == 1 ? r4.y : r4.z;
+      }
+    }
+    if (tid < 3)
+      color[3 * pix + ch] = acc / div;
+    else
+      background[3 * pix + ch] = acc / div;
+  }
+  (void)n_sorted;
+}
+
+// ------------------------------------------------------------------------------------------
+// multi-GPU film gather helpers: pack this rank's tiles into a dense slab / unpack a slab.
+// slab layout [k][10][tile_w*tile_h], k = rank-local tile ordinal, pixel order x + y*tile_w.
+// ------------------------------------------------------------------------------------------
+__global__ void k_film_pack(int W, int H, int tile_w, int tile_h, int nty, int n_tiles_total, int off, int stride,
+                            const float* __restrict__ color, const float* __restrict__ alpha,
+                            const float* __restrict__ background, const float* __restrict__ normal, float* __restrict__ slab,
+                            int unpack, float* wcolor, float* walpha, float* wbackground, float* wnormal) {
+  const int k = blockIdx.x;
+  const int tile_id = off + k * stride;
+  if (tile_id >= n_tiles_total) return;
+  const int tx = tile_id / nty, ty = tile_id % nty;
+  const int x0 = tx * tile_w, y0 = ty * tile_h;
+  const int tp = tile_w * tile_h;
+  float* sl = slab + (size_t)k * 10 * tp;
+  for (int p = threadIdx.x; p < tp; p += blockDim.x) {
+    const int xl = p % tile_w, yl = p / tile_w;
+    const int x = x0 + xl, y = y0 + yl;
+    if (x >= W || y >= H) {
+      if (!unpack)
+        for (int c = 0; c < 10; ++c) sl[c * tp + p] = 0.0f;
+      continue;
+    }
+    const size_t pix = (size_t)x + (size_t)y * W;
+    if (!unpack) {
+      for (int c = 0; c < 3; ++c) sl[c * tp + p] = color[3 * pix + c];
+      sl[3 * tp + p] = alpha[pix];
+      for (int c = 0; c < 3; ++c) sl[(4 + c) * tp + p] = background[3 * pix + c];
+      for (int c = 0; c < 3; ++c) sl[(7 + c) * tp + p] = normal[3 * pix + c];
+    } else {
+      for (int c = 0; c < 3; ++c) wcolor[3 * pix + c] = sl[c * tp + p];
+      walpha[pix] = sl[3 * tp + p];
+      for (int c = 0; c < 3; ++c) wbackground[3 * pix + c] = sl[(4 + c) * tp + p];
+      for (int c = 0; c < 3; ++c) wnormal[3 * pix + c] = sl[(7 + c) * tp + p];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// known-answer kernels (tests only)
+// ------------------------------------------------------------------------------------------
+__global__ void k_kat_detmath(int op, long long n, const float* a, const float* b, float* out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float s, c;
+  switch (op) {
+    case 0: out[i] = dm::exp(a[i]); break;
+    case 1: out[i] = dm::ln(a[i]); break;
+    case 2: out[i] = dm::pow(a[i], b[i]); break;
+    case 3: dm::sincos(a[i], &s, &c); out[i] = s; break;
+    case 4: dm::sincos(a[i], &s, &c); out[i] = c; break;
+    case 5: out[i] = dm::tan(a[i]); break;
+    case 6: out[i] = dm::atan2(a[i], b[i]); break;
+    case 7: out[i] = dm::powi5(a[i]); break;
+  }
+}
+__global__ void k_kat_sdf_dist(const RaynHitable h, long long n, const float* p3, float* out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = sdf_dist(h, mk3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]));
+}
+__global__ void k_kat_sdf_hit(const RaynHitable h, const RaynRenderConsts rc, long long n, const float* o3, const float* d3,
+                              const float* t_max, Thr thr, float* out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int ev = 0;
+  out[i] = sdf_hit(h, rc, mk3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), mk3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]), t_max[i],
+                   thr, &ev);
+}
+__global__ void k_kat_occluded(const __grid_constant__ DevScene sc, long long n, const float* s3, const float* e3, float* out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int ev = 0;
+  // reference semantics: product over all hitables (no reordering) - used to validate the
+  // early-out form in test_occluded as well
+  float acc = 1.0f;
+  const f3 a = mk3(s3[3 * i], s3[3 * i + 1], s3[3 * i + 2]), b = mk3(e3[3 * i], e3[3 * i + 1], e3[3 * i + 2]);
+  for (int k = 0; k < sc.n_hit; ++k)
+    acc = acc * (sc.hit[k].kind == RAYN_HITABLE_SPHERE ? sphere_occluded(sc.hit[k], a, b) : sdf_occluded(sc.hit[k], sc.rc, a, b, &ev));
+  const float fast = test_occluded(sc, a, b, &ev);
+  out[i] = acc == fast ? acc : -1.0f;  // -1 flags a disagreement between the two forms
+}
+__global__ void k_kat_closest_hit(const __grid_constant__ DevScene sc, Thr thr, long long n, const float* o3, const float* d3,
+                                  float* out_t, int* out_obj) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int ev = 0;
+  closest_hit(sc, mk3(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2]), mk3(d3[3 * i], d3[3 * i + 1], d3[3 * i + 2]), thr, &out_t[i],
+              &out_obj[i], &ev);
+}
+
+}  // namespace rt
