@@ -1,0 +1,135 @@
+"""Multi-GPU: film tiles shard across ranks, NCCL only for the final film gather.
+
+The reference's only parallelism is one rayon task per 16x16 tile over shared read-only state
+(film.rs:640-649); tiles never communicate (film.rs:439-627).  So one process per GPU renders
+the tiles with `tile_index % world == rank` (interleaved: fractal scenes concentrate work in
+the image centre, contiguous slabs would load-imbalance) and the film is assembled with ONE
+collective at the end of the frame: an all-gather of dense per-rank tile slabs.  Tiles are
+disjoint, so the gather moves bytes and never reduces -> the N-GPU film is bit-identical to
+the 1-GPU film.
+
+`torch.distributed` is plumbing only (process group, all_gather on device buffers).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from .film import make_frame_desc, tile_grid
+
+CHANNEL_FLOATS = (3, 1, 3, 3)  # color, alpha, background, normal (film.rs:103-120)
+
+
+def shard_tiles(n_tiles, rank, world):
+    """Tile indices (film.rs:401-425 order: tile_x * n_tiles_y + tile_y) owned by `rank`."""
+    return list(range(rank, n_tiles, world))
+
+
+def slab_floats(width, height, tile_size, rank, world):
+    return len(shard_tiles(np.prod(tile_grid(width, height, *tile_size)), rank, world)) * 10 * tile_size[0] * tile_size[1]
+
+
+def max_slab_floats(width, height, tile_size, world):
+    n = int(np.prod(tile_grid(width, height, *tile_size)))
+    return ((n + world - 1) // world) * 10 * tile_size[0] * tile_size[1]
+
+
+# ---- pack / unpack on plain arrays (host logic; used by the gloo CPU tests and as the spec
+#      the CUDA kernels k_film_pack implement) --------------------------------------------------
+def pack_tiles_numpy(planes, width, height, tile_size, rank, world):
+    tw, th = tile_size
+    ntx, nty = tile_grid(width, height, tw, th)
+    mine = shard_tiles(ntx * nty, rank, world)
+    slab = np.zeros((len(mine), 10, th, tw), np.float32)
+    chans = [planes["color"].reshape(height, width, 3), planes["alpha"].reshape(height, width, 1),
+             planes["background"].reshape(height, width, 3), planes["normal"].reshape(height, width, 3)]
+    full = np.concatenate(chans, axis=2)  # [H, W, 10]
+    for k, idx in enumerate(mine):
+        x0, y0 = (idx // nty) * tw, (idx % nty) * th
+        x1, y1 = min(x0 + tw, width), min(y0 + th, height)
+        if x0 >= width or y0 >= height:
+            continue
+        slab[k, :, : y1 - y0, : x1 - x0] = np.moveaxis(full[y0:y1, x0:x1, :], 2, 0)
+    return slab.reshape(-1)
+
+
+def unpack_tiles_numpy(slab, planes, width, height, tile_size, rank, world):
+    tw, th = tile_size
+    ntx, nty = tile_grid(width, height, tw, th)
+    mine = shard_tiles(ntx * nty, rank, world)
+    slab = np.asarray(slab, np.float32)[: len(mine) * 10 * tw * th].reshape(len(mine), 10, th, tw)
+    views = [planes["color"].reshape(height, width, 3), planes["alpha"].reshape(height, width, 1),
+             planes["background"].reshape(height, width, 3), planes["normal"].reshape(height, width, 3)]
+    for k, idx in enumerate(mine):
+        x0, y0 = (idx // nty) * tw, (idx % nty) * th
+        x1, y1 = min(x0 + tw, width), min(y0 + th, height)
+        if x0 >= width or y0 >= height:
+            continue
+        c = 0
+        for v in views:
+            nc = v.shape[2]
+            v[y0:y1, x0:x1, :] = np.moveaxis(slab[k, c:c + nc, : y1 - y0, : x1 - x0], 0, 2)
+            c += nc
+
+
+def gather_film_arrays(planes, width, height, tile_size, rank, world, all_gather):
+    """Backend-agnostic gather: `all_gather(vec) -> list of world vecs` (equal length)."""
+    n = max_slab_floats(width, height, tile_size, world)
+    mine = pack_tiles_numpy(planes, width, height, tile_size, rank, world)
+    padded = np.zeros(n, np.float32)
+    padded[: mine.size] = mine
+    for r, slab in enumerate(all_gather(padded)):
+        if r != rank:
+            unpack_tiles_numpy(slab, planes, width, height, tile_size, r, world)
+    return planes
+
+
+class DistFilm:
+    """Device-resident film of one rank + the NCCL gather.  torch is imported lazily."""
+
+    def __init__(self, renderer, width, height, tile_size, rank=0, world=1, group=None):
+        import torch
+        self.torch = torch
+        self.r, self.w, self.h, self.tile = renderer, width, height, tuple(tile_size)
+        self.rank, self.world, self.group = rank, world, group
+        dev = torch.device("cuda", renderer.device)
+        npx = width * height
+        self.store = torch.zeros(10 * npx, dtype=torch.float32, device=dev)
+        self.planes_t = {"color": self.store[: 3 * npx], "alpha": self.store[3 * npx: 4 * npx],
+                         "background": self.store[4 * npx: 7 * npx], "normal": self.store[7 * npx:]}
+        self.planes = L.RaynFilmPlanes(self.planes_t["color"].data_ptr(), self.planes_t["alpha"].data_ptr(),
+                                       self.planes_t["background"].data_ptr(), self.planes_t["normal"].data_ptr(), L.MEM_DEVICE)
+        if world > 1:
+            n = max_slab_floats(width, height, self.tile, world)
+            self.slab = torch.zeros(n, dtype=torch.float32, device=dev)
+            self.all_slabs = torch.zeros(n * world, dtype=torch.float32, device=dev)
+
+    def render(self, frame_desc):
+        """Render this rank's tiles into the device film (frame_desc carries tile_offset/stride)."""
+        self.r.render(frame_desc, self.planes)
+
+    def gather(self):
+        """All ranks end with the complete film.  One NCCL all-gather of dense tile slabs."""
+        if self.world == 1:
+            return
+        torch, lib = self.torch, L.lib()
+        import torch.distributed as dist
+        tw, th = self.tile
+        L.check(lib.rayn_b200_film_pack_tiles(self.r.ctx, self.w, self.h, tw, th, self.rank, self.world, C.byref(self.planes),
+                                              self.slab.data_ptr()), self.r.ctx)
+        dist.all_gather_into_tensor(self.all_slabs, self.slab, group=self.group)
+        torch.cuda.current_stream().synchronize()
+        n = self.slab.numel()
+        for r in range(self.world):
+            if r == self.rank:
+                continue
+            L.check(lib.rayn_b200_film_unpack_tiles(self.r.ctx, self.w, self.h, tw, th, r, self.world,
+                                                    self.all_slabs[r * n:(r + 1) * n].data_ptr(), C.byref(self.planes)), self.r.ctx)
+
+    def to_host(self):
+        return {k: v.cpu().numpy() for k, v in self.planes_t.items()}
+
+
+def device_frame_desc(inputs_dev, width, height, tile_size, samples, integrator, frame, time_range, rank, world, sets):
+    ptrs = tuple(t.data_ptr() for t in inputs_dev)
+    return make_frame_desc(width, height, tile_size, samples, integrator, frame, time_range, ptrs, L.MEM_DEVICE, rank, world, sets)
