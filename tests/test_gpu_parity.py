@@ -252,3 +252,16 @@ def test_error_codes():
         assert e.value.code == L.RAYN_ERR_INVALID_ARG
     finally:
         r.close()
+
+
+# ---- GPU vs the committed golden fixtures (tests/golden/*.npz, generated by make_golden.py) ----
+def test_gpu_matches_committed_golden(renderer):
+    import os
+    from test_cpu_oracle import GOLD, GOLDEN_CASES
+    for name, (n, res, samples, mb) in sorted(GOLDEN_CASES.items()):
+        c, inp = small_config(n, res, samples, mb)
+        renderer.upload_scene(c["world"], c["camera"])
+        g = renderer.render_host(inp, (16, 16), c["integrator"], TR)
+        gold = np.load(os.path.join(GOLD, name + ".npz"))
+        for ch in CH:
+            assert_bit_equal(g[ch], gold[ch], f"golden {name} {ch}")
