@@ -343,6 +343,11 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
   CU(cudaMemsetAsync(pb.counters, 0, 8 * sizeof(unsigned long long), st));
   int np = 2;
   while (np < spp) np <<= 1;
+  int n_sdf = 0;
+  for (int i = 0; i < n_hit; ++i) n_sdf += ctx->scene.hit[i].kind != RAYN_HITABLE_SPHERE;
+  // v2 kernels need the shadow-segment pool to hold 4 segments x every SDF hitable per lane
+  const bool simple = (ctx->flags & RAYN_FLAG_SIMPLE_MARCH) != 0 || n_sdf > SH_MAX_SDF;
+  if (!simple) CU(cudaFuncSetAttribute(k_shade2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_smem_bytes(n_sdf)));
 
   std::vector<int> h_nslots, h_slots;
   for (size_t first = 0; first < my_tiles.size(); first += tiles_per_pass) {
@@ -358,7 +363,10 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
     for (int depth = 0; depth <= mb; ++depth) {
       const Thr thr = make_thr(ctx->scene.cam, depth);
       timed_begin(ctx, RAYN_K_EXTEND);
-      k_extend<<<g_ext, 128, 0, st>>>(ctx->scene, pb, thr);
+      if (simple)
+        k_extend<<<g_ext, 128, 0, st>>>(ctx->scene, pb, thr);
+      else
+        k_extend2<<<dim3((R + EXT_CHUNK - 1) / EXT_CHUNK, nt), EXT_T, 0, st>>>(ctx->scene, pb, thr);
       timed_end(ctx, RAYN_K_EXTEND);
       timed_begin(ctx, RAYN_K_BIN);
       k_bin<<<nt, BIN_T, 0, st>>>(pb, n_hit);
@@ -377,7 +385,10 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
         }
       }
       timed_begin(ctx, RAYN_K_SHADE_PRE);
-      k_shade<<<g_shade, 128, 0, st>>>(ctx->scene, fr, pb, depth, thr);
+      if (simple)
+        k_shade<<<g_shade, 128, 0, st>>>(ctx->scene, fr, pb, depth, thr);
+      else
+        k_shade2<<<dim3((QS + SH_T - 1) / SH_T, nt), SH_T, shade_smem_bytes(n_sdf), st>>>(ctx->scene, fr, pb, depth, thr, SH_POOL * std::max(n_sdf, 1));
       timed_end(ctx, RAYN_K_SHADE_PRE);
       if (depth < mb) {
         timed_begin(ctx, RAYN_K_COMPACT);

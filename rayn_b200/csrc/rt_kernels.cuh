@@ -365,6 +365,396 @@ __global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DevScene 
   warp_add(pb.counters + CNT_SHADOW_RAYS, shadows);
 }
 
+// ==========================================================================================
+// v2 march kernels: dynamic lane refill.
+//
+// ncu on v0 (profiles/r01_v0_summary.md): issue slots 82-86 % busy with only 5-7 of 32 lanes
+// active per instruction - a warp runs until its slowest march ends.  v2 keeps ONE sdf_dist()
+// call site per loop trip and hands an idle lane the next work item as soon as its march ends,
+// so every trip evaluates the distance field on (nearly) all 32 lanes.  A march result
+// depends only on its own ray, so the order in which lanes pick up work cannot change any
+// output bit.
+// ==========================================================================================
+
+// ---- K2 v2: closest hit over a 2048-ray chunk of one tile, work pulled from a shared counter ----
+#define EXT_T 128
+#define EXT_CHUNK 2048
+__global__ void __launch_bounds__(EXT_T, 6) k_extend2(const __grid_constant__ DevScene sc, const PassBufs pb, const Thr thr) {
+  const int ts = blockIdx.y;
+  const int n = pb.n_live[ts];
+  const int chunk0 = blockIdx.x * EXT_CHUNK;
+  if (chunk0 >= n) return;
+  const int chunk1 = min(chunk0 + EXT_CHUNK, n);
+  __shared__ int s_next;
+  __shared__ RaynHitable s_hit[RAYN_MAX_HITABLES];  // shared-memory staging of the SDF / sphere constants
+  if (threadIdx.x == 0) s_next = chunk0;
+  for (int k = threadIdx.x; k < sc.n_hit; k += EXT_T) s_hit[k] = sc.hit[k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const int n_hit = sc.n_hit;
+  const float S = sc.rc.sdf_detail_scale;
+  const float c0 = 0.00005f * S, c1 = 0.05f * S;
+  const int max_marches = sc.rc.max_marches;
+  const float t_max0 = sc.rc.world_radius * 2.0f;  // film.rs:556
+
+  bool have = false, marching = false, exhausted = false;
+  f3 o = {0, 0, 0}, d = {0, 0, 0};
+  float closest = 0.0f, t = 0.0f;
+  int id = -1, hidx = 0, steps = 0, evals = 0, rays = 0;
+  size_t q = 0, g = 0;
+  while (true) {
+    __syncwarp();
+    const unsigned idle = __ballot_sync(0xffffffffu, !have);
+    if (idle && !exhausted) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s_next, __popc(idle));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const int idx = base + __popc(idle & lt);
+      if (base + __popc(idle) >= chunk1) exhausted = true;
+      if (!have && idx < chunk1) {
+        q = (size_t)ts * pb.R + idx;
+        g = (size_t)ts * pb.R + pb.q_live[q];
+        const float4 o4 = pb.o_time[g], d4 = pb.d_t[g];
+        o = mk3(o4.x, o4.y, o4.z);
+        d = mk3(d4.x, d4.y, d4.z);
+        closest = t_max0;
+        id = -1;
+        hidx = 0;
+        marching = false;
+        have = true;
+        ++rays;
+      }
+    }
+    if (!__any_sync(0xffffffffu, have)) break;
+    if (have && !marching) {  // analytic hitables up to the next SDF (hitable.rs:177-198 fold order)
+      while (hidx < n_hit && s_hit[hidx].kind == RAYN_HITABLE_SPHERE) {
+        const float ts_ = sphere_hit(s_hit[hidx], o, d, closest);
+        if (ts_ < closest) {
+          closest = ts_;
+          id = hidx;
+        }
+        ++hidx;
+      }
+      if (hidx >= n_hit) {
+        pb.d_t[g].w = closest;
+        pb.q_key[q] = id;
+        have = false;
+      }
+    }
+    if (have) {  // exactly one distance evaluation per trip: TracedSDF::hit, sdf.rs:59-83
+      const f3 p = marching ? fma3s(d, t, o) : o;
+      const float dd = sdf_dist(s_hit[hidx], p);
+      ++evals;
+      bool end = false;
+      if (!marching) {
+        t = dd;
+        steps = 0;
+        marching = true;
+        end = t != t;
+      } else {
+        const bool hit = dm::abs(dd) < dm::max(c0, c1 * thr.at(t));
+        const bool gt = t > closest;
+        if (hit || gt) {
+          end = true;
+        } else {
+          t = t + dd;
+          ++steps;
+          end = (t != t) || steps >= max_marches;
+        }
+      }
+      if (end) {
+        if (t < closest) {
+          closest = t;
+          id = hidx;
+        }
+        marching = false;
+        ++hidx;
+      }
+    }
+  }
+  warp_add(pb.counters + CNT_EXTEND_RAYS, rays);
+  warp_add(pb.counters + CNT_EVALS_EXTEND, evals);
+}
+
+// ---- K4/K5 v2: shade with a block-level shadow-segment pool ------------------------------------
+// Per round (surface NEE, then each volume march) every lane prepares its 4 light samples and
+// pushes the shadow segments that still need a sphere-march into a shared-memory pool; all
+// warps of the block then march the pool with lane refill; then each lane folds the
+// visibilities into its radiance in the reference's order.  Two exact pre-filters:
+//  * a segment whose unoccluded contribution c is all (+-0 | NaN) is not marched: c*0 and c*1
+//    are the same bits, so visibility cannot change the result (back-facing lights);
+//  * analytic spheres are tested first; product of {0,1} factors (hitable.rs:164-168).
+#define SH_T 128
+#define SH_POOL (SH_T * 4)
+#define SH_MAX_SDF 4
+struct ShadeSmem {
+  RaynHitable hit[RAYN_MAX_HITABLES];
+  RaynMaterial mat[RAYN_MAX_MATERIALS];
+  RaynLight light[RAYN_MAX_LIGHTS];
+  float vis[SH_POOL];
+  float cx[4][SH_T], cy[4][SH_T], cz[4][SH_T], cden[4][SH_T], ctr[4][SH_T];
+  int n, next;
+  int pad_[2];
+  // followed by float4 pa[pool_cap] (start.xyz, max_dist) and float4 pb[pool_cap] (dir.xyz, bits(owner | hidx << 16)),
+  // pool_cap = SH_POOL * number of SDF hitables
+};
+static_assert(sizeof(ShadeSmem) % 16 == 0, "pool must stay float4 aligned");
+static inline size_t shade_smem_bytes(int n_sdf) { return sizeof(ShadeSmem) + (size_t)2 * SH_POOL * (n_sdf > 0 ? n_sdf : 1) * sizeof(float4); }
+
+__global__ void __launch_bounds__(SH_T, 4) k_shade2(const __grid_constant__ DevScene sc, const DevFrame fr, const PassBufs pb,
+                                                    const int depth, const Thr thr, const int pool_cap) {
+  extern __shared__ __align__(16) unsigned char sh_raw[];
+  ShadeSmem& sm = *reinterpret_cast<ShadeSmem*>(sh_raw);
+  float4* __restrict__ s_pa = reinterpret_cast<float4*>(sh_raw + sizeof(ShadeSmem));
+  float4* __restrict__ s_pb = s_pa + pool_cap;
+  const int ts = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+  const int s = blockIdx.x * SH_T + tid;
+  const int nslots = pb.n_slots[ts];
+  if (blockIdx.x * SH_T >= nslots) return;  // block-uniform
+  for (int k = tid; k < sc.n_hit; k += SH_T) sm.hit[k] = sc.hit[k];
+  for (int k = tid; k < sc.n_mat; k += SH_T) sm.mat[k] = sc.mat[k];
+  for (int k = tid; k < sc.n_lights; k += SH_T) sm.light[k] = sc.light[k];
+  int* __restrict__ qs = pb.q_shade + (size_t)ts * pb.QS;
+  const int id = s < nslots ? qs[s] : -1;
+  const bool valid = id >= 0;
+  const TileGeom tg = tile_geom(fr, pb.tile_ids[ts]);
+  int sample = 0;
+  float scramble = 0.0f;
+  if (valid) {
+    const int pl = id / fr.spp;
+    sample = id - pl * fr.spp;
+    const int xl = pl / tg.th, yl = pl - xl * tg.th;
+    scramble = __ldg(fr.scramble + (tg.x0 + xl) + (size_t)(tg.y0 + yl) * fr.W);
+  }
+  const int n1 = 3 + fr.vm, n2h = (12 + 8 * fr.vm) / 2;
+  const int set1 = 1 + depth * n1, set2 = 2 + depth * n2h;
+  const int nl = sc.n_lights;
+  unsigned pack = 0;
+  if (nl > 0)
+    pack = (unsigned)light_index(samp1(fr, sample, scramble, set1 + 0), nl) | ((unsigned)light_index(samp1(fr, sample, scramble, set1 + 1), nl) << 8) |
+           ((unsigned)light_index(samp1(fr, sample, scramble, set1 + 2), nl) << 16);
+  // w[r] = the 4 light indices of round r, one byte per packet lane (integrator.rs:76-77,100-102)
+  unsigned w0 = 0, w1 = 0, w2 = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const unsigned pk = __shfl_sync(0xffffffffu, pack, (lane & ~3) + k);
+    w0 |= (pk & 0xffu) << (8 * k);
+    w1 |= ((pk >> 8) & 0xffu) << (8 * k);
+    w2 |= ((pk >> 16) & 0xffu) << (8 * k);
+  }
+  __syncthreads();  // staged constants visible
+
+  int evals = 0, shadows = 0;
+  ShadingPoint sp;
+  f3 radiance = {0, 0, 0}, throughput = {0, 0, 0}, wo = {0, 0, 0};
+  float vt = 1.0f;
+  bool recv = false;
+  int mat_idx = 0;
+  size_t g = 0;
+  const bool has_ext = sc.vol.has_extinction != 0;
+  const float neg_rho_t = -sc.vol.coeff_extinction;
+  if (valid) {
+    const int* __restrict__ bs = pb.bin_start + ts * (RAYN_MAX_HITABLES + 1);
+    int obj = 0;
+    while (obj + 1 < sc.n_hit && s >= bs[obj + 1]) ++obj;
+    const RaynHitable& h = sm.hit[obj];
+    mat_idx = h.material;
+    g = (size_t)ts * pb.R + id;
+    const float4 o4 = pb.o_time[g], d4 = pb.d_t[g], r4 = pb.rad[g], t4 = pb.thr[g];
+    sp.o = mk3(o4.x, o4.y, o4.z);
+    sp.d = mk3(d4.x, d4.y, d4.z);
+    sp.time = o4.w;
+    sp.t = d4.w;
+    shading_info(sc, h, thr, sp, &evals);
+    radiance = mk3(r4.x, r4.y, r4.z);
+    throughput = mk3(t4.x, t4.y, t4.z);
+    wo = -sp.d;
+    vt = has_ext ? dm::exp(neg_rho_t * sp.t) : 1.0f;            // integrator.rs:64-68
+    radiance = radiance + bsdf_le(sm.mat[mat_idx], wo) * throughput * vt;  // :70-71
+    recv = receives_light(sm.mat[mat_idx]);
+  }
+  warp_add(pb.counters + CNT_SHADE_LANES, valid ? 1 : 0);
+
+  const bool scat = sc.vol.has_scattering != 0 && nl > 0;
+  const int n_rounds = nl > 0 ? 1 + (scat ? fr.vm : 0) : 0;
+  const float S = sc.rc.sdf_detail_scale;
+  const float oc0 = 0.0001f * S, oc1 = 0.00001f * S;
+  const int max_vis = sc.rc.max_vis_marches;
+  for (int round = 0; round < n_rounds; ++round) {
+    if (tid == 0) {
+      sm.n = 0;
+      sm.next = 0;
+    }
+    __syncthreads();
+    const bool act = valid && (round == 0 ? recv : true);
+    const unsigned wr = round == 0 ? w0 : (round == 1 ? w1 : w2);
+    if (act) {
+      const float vol_sample = round == 0 ? 0.0f : samp1(fr, sample, scramble, set1 + 1);  // samples_1d[1], :115
+#pragma unroll 1
+      for (int i = 0; i < 4; ++i) {
+        const int li_idx = (int)((wr >> (8 * i)) & 0xffu);
+        const RaynLight& L = sm.light[li_idx];
+        const int set = round == 0 ? set2 + i : set2 + 4 + 4 * (round - 1) + i;
+        const float u0 = samp2(fr, 0, sample, scramble, set), u1 = samp2(fr, 1, sample, scramble, set);
+        f3 start, end_point, li, c;
+        float den, trans = 1.0f;
+        if (round == 0) {  // surface_sample_one_light :207-240
+          float pdf;
+          light_sample(L, u0, u1, sp.point, &end_point, &li, &pdf);
+          f3 wi = end_point - sp.point;
+          const float dist = mag(wi);
+          wi = wi / dist;
+          start = sp.point + sp.normal * dm::signum(dot(sp.normal, wi)) * sp.offset_by;
+          const f3 f = bsdf_f(sm.mat[mat_idx], wo, wi, sp.normal) * dm::max(dot(sp.normal, wi), 0.0f);
+          const float tr = has_ext ? dm::exp(neg_rho_t * dist) : 1.0f;
+          c = li * f * tr;
+          den = pdf;
+        } else {  // volume_sample_one_light :242-281
+          float vol_dist, vol_pdf, light_pdf;
+          light_sample_volume(L, vol_sample, sp.o, sp.d, sp.t, &vol_dist, &vol_pdf);
+          start = sp.o + sp.d * vol_dist;
+          light_sample(L, u0, u1, start, &end_point, &li, &light_pdf);
+          const float dist_point_to_light = mag(end_point - start);
+          const float f = 1.0f / (4.0f * RT_PI);
+          const float tr = has_ext ? dm::exp(neg_rho_t * dist_point_to_light) : 1.0f;
+          c = li * f * tr;
+          den = vol_pdf * light_pdf;
+          trans = has_ext ? dm::exp(neg_rho_t * vol_dist) : 1.0f;  // :122-126
+        }
+        sm.cx[i][tid] = c.x, sm.cy[i][tid] = c.y, sm.cz[i][tid] = c.z, sm.cden[i][tid] = den, sm.ctr[i][tid] = trans;
+        ++shadows;
+        float vis = 1.0f;
+        const bool irrelevant = (c.x == 0.0f || c.x != c.x) && (c.y == 0.0f || c.y != c.y) && (c.z == 0.0f || c.z != c.z);
+        if (!irrelevant) {
+          for (int k = 0; k < sc.n_hit && vis != 0.0f; ++k)
+            if (sm.hit[k].kind == RAYN_HITABLE_SPHERE) vis = sphere_occluded(sm.hit[k], start, end_point);
+          if (vis != 0.0f) {
+            f3 dir = end_point - start;  // TracedSDF::occluded prologue, sdf.rs:26-28
+            const float max_dist = mag(dir);
+            dir = dir / max_dist;
+            for (int k = 0; k < sc.n_hit; ++k)
+              if (sm.hit[k].kind != RAYN_HITABLE_SPHERE) {
+                const int slot = atomicAdd(&sm.n, 1);
+                s_pa[slot] = make_float4(start.x, start.y, start.z, max_dist);
+                s_pb[slot] = make_float4(dir.x, dir.y, dir.z, __int_as_float((tid * 4 + i) | (k << 16)));
+              }
+          }
+        }
+        sm.vis[tid * 4 + i] = vis;
+      }
+    }
+    __syncthreads();
+    {  // ---- cooperative sphere-march of the pool: TracedSDF::occluded, sdf.rs:25-57 / SURVEY §9.2
+      const int pool_n = sm.n;
+      const unsigned lt = (1u << lane) - 1u;
+      bool have = false, first = false, exhausted = false;
+      f3 st = {0, 0, 0}, dir = {0, 0, 0};
+      float max_dist = 0.0f, t = 0.0f;
+      int owner = 0, hk = 0, steps = 0;
+      while (true) {
+        __syncwarp();
+        const unsigned idle = __ballot_sync(0xffffffffu, !have);
+        if (idle && !exhausted) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&sm.next, __popc(idle));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          const int idx = base + __popc(idle & lt);
+          if (base + __popc(idle) >= pool_n) exhausted = true;
+          if (!have && idx < pool_n) {
+            const float4 a = s_pa[idx], b = s_pb[idx];
+            st = mk3(a.x, a.y, a.z);
+            max_dist = a.w;
+            dir = mk3(b.x, b.y, b.z);
+            const int ow = __float_as_int(b.w);
+            owner = ow & 0xffff;
+            hk = ow >> 16;
+            first = true;
+            have = true;
+          }
+        }
+        if (!__any_sync(0xffffffffu, have)) break;
+        if (have) {
+          const f3 p = first ? st : fma3s(dir, t, st);
+          const float dd = sdf_dist(sm.hit[hk], p);
+          ++evals;
+          bool done = false;
+          if (first) {
+            t = dd;
+            first = false;
+            steps = 0;
+            done = (t != t) || (t > max_dist);
+          } else if (dm::abs(dd) < dm::max(oc0, oc1 * t)) {
+            sm.vis[owner] = 0.0f;  // occluded (only ever written as 0: product semantics)
+            done = true;
+          } else {
+            t = t + dd;
+            ++steps;
+            done = (t != t) || steps >= max_vis || (t > max_dist);
+          }
+          if (done) have = false;
+        }
+      }
+    }
+    __syncthreads();
+    if (act) {
+      if (round == 0) {
+        const float correction = (float)nl / 4.0f;  // :79-80
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+          const f3 contrib = mk3(sm.cx[i][tid], sm.cy[i][tid], sm.cz[i][tid]) * sm.vis[tid * 4 + i] / sm.cden[i][tid];
+          radiance = radiance + contrib * throughput * correction * vt;  // :91-92
+        }
+      } else {
+        const float rho_s = sc.vol.coeff_scattering;
+        const float correction = (float)nl / 4.0f / (float)fr.vm;  // :104-108
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+          const f3 contrib = mk3(sm.cx[i][tid], sm.cy[i][tid], sm.cz[i][tid]) * sm.vis[tid * 4 + i] / sm.cden[i][tid];
+          radiance = radiance + contrib * throughput * correction * rho_s * sm.ctr[i][tid];  // :128-129
+        }
+      }
+    }
+  }
+
+  if (valid) {
+    const RaynMaterial& mat = sm.mat[mat_idx];
+    if (recv) {  // :134-188
+      const int setb = set2 + 4 + 4 * fr.vm;
+      const Scatter se = bsdf_scatter(mat, wo, sp, samp1(fr, sample, scramble, set1 + 3), samp2(fr, 0, sample, scramble, setb),
+                                      samp2(fr, 1, sample, scramble, setb), samp2(fr, 0, sample, scramble, setb + 1),
+                                      samp2(fr, 1, sample, scramble, setb + 1));
+      const float ndl = dm::abs(dot(se.wi, sp.normal));
+      f3 new_throughput = throughput * vt * se.f * ndl / se.pdf;
+      float roulette_factor = 0.0f;
+      if (depth > 2) {
+        roulette_factor = dm::max(1.0f - component_max(throughput), 0.05f);
+        new_throughput = new_throughput / (1.0f - roulette_factor);
+      }
+      if (depth == 0) pb.nrm0[g] = make_float4(sp.normal.x, sp.normal.y, sp.normal.z, __uint_as_float((unsigned)s + 1u));
+      const float roulette_sample = samp1(fr, sample, scramble, set1 + 4);
+      if (depth >= fr.max_bounces || roulette_sample < roulette_factor) {
+        pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+        pb.term[g] = (TERM_COLOR << 30) | ((unsigned)depth << 20) | (unsigned)s;
+        qs[s] = -1;
+      } else {
+        const f3 no = sp.point + sp.normal * dm::signum(dot(sp.normal, se.wi)) * sp.offset_by;
+        if (!any_nan(new_throughput)) throughput = new_throughput;
+        pb.o_time[g] = make_float4(no.x, no.y, no.z, sp.time);
+        pb.d_t[g] = make_float4(se.wi.x, se.wi.y, se.wi.z, 0.0f);
+        pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+        pb.thr[g] = make_float4(throughput.x, throughput.y, throughput.z, 0.0f);
+      }
+    } else {  // :189-203
+      pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+      pb.term[g] = ((depth == 0 ? TERM_BACKGROUND : TERM_COLOR) << 30) | ((unsigned)depth << 20) | (unsigned)s;
+      qs[s] = -1;
+    }
+  }
+  warp_add(pb.counters + CNT_EVALS_SHADOW, evals);
+  warp_add(pb.counters + CNT_SHADOW_RAYS, shadows);
+}
+
 // ------------------------------------------------------------------------------------------
 // K6 compact: film.rs:604-625.  Order-preserving stream compaction of the surviving slots of
 // a tile into the next live queue: per-warp __ballot_sync + popc prefix, cross-warp offsets
