@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--max-paths", type=int, default=0)
+    ap.add_argument("--flags", type=int, default=0, help="RAYN_FLAG_* kernel-family selection (2 = v0 simple, 4 = v2 block pools)")
     return ap.parse_args()
 
 
@@ -212,7 +213,7 @@ def main():
 
     # ---- resident inputs + film ---------------------------------------------------------------
     inputs_dev = [torch.from_numpy(a).to(dev) for a in inputs.arrays()]
-    r = Renderer(local_rank, max_paths_per_pass=args.max_paths)
+    r = Renderer(local_rank, max_paths_per_pass=args.max_paths, flags=args.flags)
     r.upload_scene(c["world"], c["camera"])
     film = DistFilm(r, w, h, tile, rank, world)
     fdesc = device_frame_desc(inputs_dev, w, h, tile, c["samples"], c["integrator"], 1, c["time_range"], rank, world, sets)
@@ -267,7 +268,7 @@ def main():
     value = total_samples / (ms_per_step * 1e-3) / 1e6
 
     # ---- per-kernel breakdown + roofline (separate TIMING context so events do not perturb `value`) ----
-    rt = Renderer(local_rank, max_paths_per_pass=args.max_paths, flags=L.FLAG_TIMING)
+    rt = Renderer(local_rank, max_paths_per_pass=args.max_paths, flags=L.FLAG_TIMING | args.flags)
     rt.upload_scene(c["world"], c["camera"])
     filmt = DistFilm(rt, w, h, tile, rank, world)
     filmt.render(fdesc)
@@ -281,35 +282,39 @@ def main():
     sdf = [hh for hh in c["world"].hitables.items if hasattr(hh, "sdf")]
     iters = sdf[0].sdf.iterations if sdf else 0
     flop_eval = (MANDELBULB_FLOP_PER_ITER if is_bulb else MANDELBOX_FLOP_PER_ITER) * iters + 10
+    ALG_BYTES_SHADOW = 40.0  # read seg_a + seg_b + owner (36 B), clear one visibility bit (4 B)
     ext_s = kms.get("extend", 0.0) * 1e-3
-    shade_s = kms.get("shade_pre", 0.0) * 1e-3
-    dom = max(kms, key=kms.get) if kms else "extend"
-    per_kernel = {
-        "extend(sphere-march)": {"ms": kms.get("extend", 0.0), "share": kms.get("extend", 0.0) / max(ksum, 1e-9), "rays": int(ts.extend_rays),
-                                  "hbm_gbs_algorithmic": ts.extend_rays * ALG_BYTES_EXTEND / max(ext_s, 1e-12) / 1e9,
-                                  "sdf_evals": int(ts.sdf_evals_extend),
-                                  "fp32_tflops_algorithmic": ts.sdf_evals_extend * flop_eval / max(ext_s, 1e-12) / 1e12},
-        "shade(+shadow march)": {"ms": kms.get("shade_pre", 0.0), "share": kms.get("shade_pre", 0.0) / max(ksum, 1e-9), "lanes": int(ts.shade_lanes),
-                                 "shadow_rays": int(ts.shadow_rays), "sdf_evals": int(ts.sdf_evals_shadow),
-                                 "hbm_gbs_algorithmic": ts.shade_lanes * ALG_BYTES_SHADE / max(shade_s, 1e-12) / 1e9,
-                                 "fp32_tflops_algorithmic": ts.sdf_evals_shadow * flop_eval / max(shade_s, 1e-12) / 1e12},
-    }
+    shadow_s = kms.get("shadow", 0.0) * 1e-3
+    fused_shade = "shadow" not in kms  # v0/v2 kernel families fuse the shadow march into shade
+    shade_s = (kms.get("shade_pre", 0.0) + kms.get("shade_post", 0.0)) * 1e-3
+    per_kernel = {}
     for k in kms:
-        if k not in ("extend", "shade_pre"):
-            per_kernel[k] = {"ms": kms[k], "share": kms[k] / max(ksum, 1e-9)}
-    if dom == "shade_pre":
-        achieved = per_kernel["shade(+shadow march)"]["hbm_gbs_algorithmic"]
-        dom_name, dom_launches = "k_shade", klaunch.get("shade_pre", 1)
-    else:
-        achieved = per_kernel["extend(sphere-march)"]["hbm_gbs_algorithmic"]
-        dom_name, dom_launches = "k_extend", klaunch.get("extend", 1)
+        per_kernel[k] = {"ms": kms[k], "share": kms[k] / max(ksum, 1e-9), "launches": klaunch[k]}
+    per_kernel.setdefault("extend", {}).update(
+        rays=int(ts.extend_rays), sdf_evals=int(ts.sdf_evals_extend),
+        hbm_gbs_algorithmic=ts.extend_rays * ALG_BYTES_EXTEND / max(ext_s, 1e-12) / 1e9,
+        fp32_tflops_algorithmic=ts.sdf_evals_extend * flop_eval / max(ext_s, 1e-12) / 1e12)
+    sh_key = "shade_pre" if fused_shade else "shadow"
+    sh_s = shade_s if fused_shade else shadow_s
+    per_kernel.setdefault(sh_key, {}).update(
+        shadow_rays=int(ts.shadow_rays), sdf_evals=int(ts.sdf_evals_shadow),
+        hbm_gbs_algorithmic=(ts.shade_lanes * ALG_BYTES_SHADE if fused_shade else ts.shadow_rays * ALG_BYTES_SHADOW) / max(sh_s, 1e-12) / 1e9,
+        fp32_tflops_algorithmic=ts.sdf_evals_shadow * flop_eval / max(sh_s, 1e-12) / 1e12)
+    if not fused_shade:
+        per_kernel["shade_pre"]["lanes"] = int(ts.shade_lanes)
+        per_kernel["shade_pre"]["hbm_gbs_algorithmic"] = ts.shade_lanes * ALG_BYTES_SHADE / max(shade_s, 1e-12) / 1e9
+    dom = max(kms, key=kms.get) if kms else "extend"
+    dom_name = {"extend": "k_extend3 (closest-hit sphere-march)", "shadow": "k_shadow (occlusion sphere-march)",
+                "shade_pre": "k_shade_pre", "shade_post": "k_shade_post"}.get(dom, dom)
+    achieved = per_kernel[dom].get("hbm_gbs_algorithmic", 0.0)
     roofline = {"kernel": dom_name, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                 "peak_source": peak_src, "traffic": None,
-                "note": "march kernels are FP32-ALU/divergence bound, not HBM bound (SURVEY F7); fp32 fraction reported alongside",
+                "note": "march kernels are FP32-issue/divergence bound, not HBM bound (SURVEY F7): achieved = algorithmic bytes / kernel time; "
+                        "fp32 fraction of the non-tensor peak reported alongside",
                 "fp32_peak_tflops_nominal": FP32_PEAK_TFLOPS,
-                "fp32_frac_extend": per_kernel["extend(sphere-march)"]["fp32_tflops_algorithmic"] / FP32_PEAK_TFLOPS,
-                "fp32_frac_shade": per_kernel["shade(+shadow march)"]["fp32_tflops_algorithmic"] / FP32_PEAK_TFLOPS,
-                "launches_of_kernel_per_step": dom_launches}
+                "fp32_frac_extend": per_kernel["extend"].get("fp32_tflops_algorithmic", 0.0) / FP32_PEAK_TFLOPS,
+                "fp32_frac_shadow": per_kernel[sh_key].get("fp32_tflops_algorithmic", 0.0) / FP32_PEAK_TFLOPS,
+                "launches_of_kernel_per_step": klaunch.get(dom, 0)}
     rt.close()
     del filmt
 

@@ -191,7 +191,9 @@ typedef struct RaynConfig {
 } RaynConfig;
 
 #define RAYN_FLAG_TIMING 1       /* record per-kernel CUDA-event times into RaynStats      */
-#define RAYN_FLAG_SIMPLE_MARCH 2 /* one-thread-per-ray march kernels (no lane refill)      */
+#define RAYN_FLAG_SIMPLE_MARCH 2 /* v0: one-thread-per-ray march kernels (no lane refill)  */
+#define RAYN_FLAG_BLOCK_POOL 4   /* v2: per-block refill / shadow pool instead of the
+                                    pass-wide persistent march kernels (v3, default)       */
 
 #define RAYN_STAT_KERNELS 12
 typedef struct RaynStats {

@@ -30,10 +30,13 @@ struct RaynContext {
   DevScene scene;
   int64_t cap_paths = 0;  // requested paths per pass
   // pass buffers
-  int64_t alloc_paths = 0, alloc_q = 0;
+  int64_t alloc_paths = 0, alloc_q = 0, alloc_seg = 0;
   int alloc_tiles = 0;
   PassBufs pb;
   int* d_tile_ids = nullptr;
+  int* d_batch_prefix = nullptr;  // [alloc_tiles + 1]
+  int* d_work_ctr = nullptr;      // [4] global work counters of the persistent kernels
+  int n_sm = 148;
   // staging for host-space inputs / outputs
   float *d_s1 = nullptr, *d_s2 = nullptr, *d_scr = nullptr, *d_fis = nullptr;
   size_t cap_s1 = 0, cap_s2 = 0, cap_scr = 0;
@@ -81,17 +84,21 @@ static void free_pass(RaynContext* c) {
   cudaFree(p.o_time), cudaFree(p.d_t), cudaFree(p.rad), cudaFree(p.thr), cudaFree(p.nrm0), cudaFree(p.term);
   cudaFree(p.q_live), cudaFree(p.q_key), cudaFree(p.q_shade), cudaFree(p.n_live), cudaFree(p.n_slots), cudaFree(p.bin_start);
   cudaFree(c->d_tile_ids);
+  cudaFree(c->d_batch_prefix);
+  c->d_batch_prefix = nullptr;
+  cudaFree(p.nrm), cudaFree(p.vis), cudaFree(p.seg_a), cudaFree(p.seg_b), cudaFree(p.seg_owner);
   unsigned long long* counters = p.counters;
   memset(&p, 0, sizeof p);
   p.counters = counters;
   c->d_tile_ids = nullptr;
-  c->alloc_paths = c->alloc_q = 0;
+  c->alloc_paths = c->alloc_q = c->alloc_seg = 0;
   c->alloc_tiles = 0;
 }
 
-static int32_t ensure_pass(RaynContext* ctx, int n_tiles, int R, int QS) {
+static int32_t ensure_pass(RaynContext* ctx, int n_tiles, int R, int QS, int seg_per_path) {
   const int64_t need_paths = (int64_t)n_tiles * R, need_q = (int64_t)n_tiles * QS;
-  if (need_paths <= ctx->alloc_paths && need_q <= ctx->alloc_q && n_tiles <= ctx->alloc_tiles) return RAYN_OK;
+  const int64_t need_seg = need_paths * seg_per_path;
+  if (need_paths <= ctx->alloc_paths && need_q <= ctx->alloc_q && n_tiles <= ctx->alloc_tiles && need_seg <= ctx->alloc_seg) return RAYN_OK;
   free_pass(ctx);
   PassBufs& p = ctx->pb;
   CU(cudaMalloc(&p.o_time, need_paths * sizeof(float4)));
@@ -107,6 +114,16 @@ static int32_t ensure_pass(RaynContext* ctx, int n_tiles, int R, int QS) {
   CU(cudaMalloc(&p.n_slots, n_tiles * sizeof(int)));
   CU(cudaMalloc(&p.bin_start, (size_t)n_tiles * (RAYN_MAX_HITABLES + 1) * sizeof(int)));
   CU(cudaMalloc(&ctx->d_tile_ids, n_tiles * sizeof(int)));
+  CU(cudaMalloc(&ctx->d_batch_prefix, ((size_t)n_tiles + 1) * sizeof(int)));
+  CU(cudaMalloc(&p.nrm, need_paths * sizeof(float4)));
+  CU(cudaMalloc(&p.vis, need_paths * sizeof(uint32_t)));
+  if (need_seg > 0) {
+    CU(cudaMalloc(&p.seg_a, need_seg * sizeof(float4)));
+    CU(cudaMalloc(&p.seg_b, need_seg * sizeof(float4)));
+    CU(cudaMalloc(&p.seg_owner, need_seg * sizeof(int)));
+  }
+  p.seg_cap = need_seg;
+  ctx->alloc_seg = need_seg;
   ctx->alloc_paths = need_paths;
   ctx->alloc_q = need_q;
   ctx->alloc_tiles = n_tiles;
@@ -178,6 +195,8 @@ int32_t rayn_b200_create(const RaynConfig* cfg, RaynContext** out_ctx) {
   cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMalloc(&ctx->pb.counters, 8 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_fis, RAYN_FIS_TABLE_SIZE * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_work_ctr, 4 * sizeof(int));
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, dev);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
   if (e != cudaSuccess) {
@@ -195,6 +214,7 @@ void rayn_b200_destroy(RaynContext* ctx) {
   cudaStreamSynchronize(ctx->stream);
   free_pass(ctx);
   cudaFree(ctx->pb.counters);
+  cudaFree(ctx->d_work_ctr);
   cudaFree(ctx->d_s1), cudaFree(ctx->d_s2), cudaFree(ctx->d_scr), cudaFree(ctx->d_fis), cudaFree(ctx->d_planes);
   for (auto& t : ctx->timed) cudaEventDestroy(t.a), cudaEventDestroy(t.b);
   cudaEventDestroy(ctx->ev0), cudaEventDestroy(ctx->ev1);
@@ -336,18 +356,24 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
   int tiles_per_pass = (int)std::max<int64_t>(1, ctx->cap_paths / R);
   tiles_per_pass = std::min(tiles_per_pass, 65535);
   tiles_per_pass = std::min<int>(tiles_per_pass, std::max<size_t>(my_tiles.size(), 1));
-  int32_t rc = ensure_pass(ctx, tiles_per_pass, R, QS);
+  int n_sdf = 0;
+  for (int i = 0; i < n_hit; ++i) n_sdf += ctx->scene.hit[i].kind != RAYN_HITABLE_SPHERE;
+  // kernel family: v3 (default) pass-wide persistent march kernels; v2 per-block pools; v0 one thread per ray
+  const bool simple = (ctx->flags & RAYN_FLAG_SIMPLE_MARCH) != 0;
+  const bool block_pool = !simple && (ctx->flags & RAYN_FLAG_BLOCK_POOL) != 0 && n_sdf <= SH_MAX_SDF;
+  const bool v3 = !simple && !block_pool;
+  const bool volume_on = ctx->scene.vol.has_scattering != 0 && ctx->scene.n_lights > 0;
+  const int seg_per_path = v3 ? (volume_on ? 4 * (1 + vm) : 4) * n_sdf : 0;  // worst case shadow segments per path per depth
+  if (v3 && volume_on) tiles_per_pass = std::max(1, tiles_per_pass / 3);
+  int32_t rc = ensure_pass(ctx, tiles_per_pass, R, QS, seg_per_path);
   if (rc) return rc;
   PassBufs pb = ctx->pb;
   pb.R = R, pb.QS = QS, pb.tile_ids = ctx->d_tile_ids;
+  pb.seg_count = ctx->d_work_ctr + 2;
   CU(cudaMemsetAsync(pb.counters, 0, 8 * sizeof(unsigned long long), st));
   int np = 2;
   while (np < spp) np <<= 1;
-  int n_sdf = 0;
-  for (int i = 0; i < n_hit; ++i) n_sdf += ctx->scene.hit[i].kind != RAYN_HITABLE_SPHERE;
-  // v2 kernels need the shadow-segment pool to hold 4 segments x every SDF hitable per lane
-  const bool simple = (ctx->flags & RAYN_FLAG_SIMPLE_MARCH) != 0 || n_sdf > SH_MAX_SDF;
-  if (!simple) CU(cudaFuncSetAttribute(k_shade2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_smem_bytes(n_sdf)));
+  if (block_pool) CU(cudaFuncSetAttribute(k_shade2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_smem_bytes(n_sdf)));
 
   std::vector<int> h_nslots, h_slots;
   for (size_t first = 0; first < my_tiles.size(); first += tiles_per_pass) {
@@ -363,10 +389,16 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
     for (int depth = 0; depth <= mb; ++depth) {
       const Thr thr = make_thr(ctx->scene.cam, depth);
       timed_begin(ctx, RAYN_K_EXTEND);
-      if (simple)
+      if (simple) {
         k_extend<<<g_ext, 128, 0, st>>>(ctx->scene, pb, thr);
-      else
+      } else if (block_pool) {
         k_extend2<<<dim3((R + EXT_CHUNK - 1) / EXT_CHUNK, nt), EXT_T, 0, st>>>(ctx->scene, pb, thr);
+      } else {
+        k_scan_live<<<1, SCAN_T, 0, st>>>(pb, ctx->d_batch_prefix, ctx->d_work_ctr);
+        ctx->stats.launches++;
+        ctx->stats.kernel_launches[RAYN_K_MISC]++;
+        k_extend3<<<ctx->n_sm * 8, EXT_T, 0, st>>>(ctx->scene, pb, thr, ctx->d_batch_prefix, ctx->d_work_ctr);
+      }
       timed_end(ctx, RAYN_K_EXTEND);
       timed_begin(ctx, RAYN_K_BIN);
       k_bin<<<nt, BIN_T, 0, st>>>(pb, n_hit);
@@ -384,12 +416,26 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
           for (int s = 0; s < h_nslots[t]; ++s) ctx->qlog.push_back(h_slots[(size_t)t * QS + s]);
         }
       }
-      timed_begin(ctx, RAYN_K_SHADE_PRE);
-      if (simple)
-        k_shade<<<g_shade, 128, 0, st>>>(ctx->scene, fr, pb, depth, thr);
-      else
-        k_shade2<<<dim3((QS + SH_T - 1) / SH_T, nt), SH_T, shade_smem_bytes(n_sdf), st>>>(ctx->scene, fr, pb, depth, thr, SH_POOL * std::max(n_sdf, 1));
-      timed_end(ctx, RAYN_K_SHADE_PRE);
+      if (v3) {
+        timed_begin(ctx, RAYN_K_SHADE_PRE);
+        k_shade_pre<<<g_shade, 128, 0, st>>>(ctx->scene, fr, pb, depth, thr);
+        timed_end(ctx, RAYN_K_SHADE_PRE);
+        if (n_sdf > 0 && ctx->scene.n_lights > 0) {
+          timed_begin(ctx, RAYN_K_SHADOW);
+          k_shadow<<<ctx->n_sm * 8, SHD_T, 0, st>>>(ctx->scene, pb, ctx->d_work_ctr + 1);
+          timed_end(ctx, RAYN_K_SHADOW);
+        }
+        timed_begin(ctx, RAYN_K_SHADE_POST);
+        k_shade_post<<<g_shade, 128, 0, st>>>(ctx->scene, fr, pb, depth);
+        timed_end(ctx, RAYN_K_SHADE_POST);
+      } else {
+        timed_begin(ctx, RAYN_K_SHADE_PRE);
+        if (simple)
+          k_shade<<<g_shade, 128, 0, st>>>(ctx->scene, fr, pb, depth, thr);
+        else
+          k_shade2<<<dim3((QS + SH_T - 1) / SH_T, nt), SH_T, shade_smem_bytes(n_sdf), st>>>(ctx->scene, fr, pb, depth, thr, SH_POOL * std::max(n_sdf, 1));
+        timed_end(ctx, RAYN_K_SHADE_PRE);
+      }
       if (depth < mb) {
         timed_begin(ctx, RAYN_K_COMPACT);
         k_compact<<<nt, CMP_T, 0, st>>>(pb);

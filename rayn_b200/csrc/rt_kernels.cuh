@@ -48,6 +48,14 @@ struct PassBufs {
   int* n_slots;    // [n_tiles]
   int* bin_start;  // [n_tiles*(RAYN_MAX_HITABLES+1)]
   unsigned long long* counters;  // [8] stats
+  // v3 shading split (pre -> persistent shadow march -> post)
+  float4* nrm;        // [paths] shading normal.xyz, offset_by of the current depth (hitable.rs:21-28)
+  uint32_t* vis;      // [paths] bit i = light sample i of this depth is visible
+  float4* seg_a;      // [seg_cap] shadow segment start.xyz, max_dist
+  float4* seg_b;      // [seg_cap] dir.xyz, bits(sample i | hitable << 8)
+  int* seg_owner;     // [seg_cap] path index g
+  int* seg_count;     // [1] segments pushed this depth
+  long long seg_cap;
 };
 
 enum { CNT_EXTEND_RAYS = 0, CNT_SHADE_LANES = 1, CNT_SHADOW_RAYS = 2, CNT_EVALS_EXTEND = 3, CNT_EVALS_SHADOW = 4 };
@@ -477,6 +485,163 @@ __global__ void __launch_bounds__(EXT_T, 6) k_extend2(const __grid_constant__ De
   warp_add(pb.counters + CNT_EVALS_EXTEND, evals);
 }
 
+// ---- K2 v3: persistent closest-hit kernel.  v2 still idles lanes at the tail of every 2048-ray
+// chunk (ncu r1v2: 19 of 32 lanes at the distance-eval site).  v3 flattens the per-tile live
+// lists into 128-ray batches numbered across the whole pass (k_scan_live builds the prefix),
+// and resident warps pull batches from ONE global counter until the pass is drained: the only
+// tail left is at the very end of the kernel.
+#define EXT_BATCH 128
+#define SCAN_T 1024
+__global__ void __launch_bounds__(SCAN_T) k_scan_live(const PassBufs pb, int* __restrict__ batch_prefix, int* __restrict__ work_ctr) {
+  // batch_prefix[ts] = sum_{u<ts} ceil(n_live[u] / EXT_BATCH); batch_prefix[n_tiles] = total
+  __shared__ int wsum[SCAN_T / 32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    carry = 0;
+    work_ctr[0] = 0;  // extend batches
+    work_ctr[1] = 0;  // shadow batches
+    work_ctr[2] = 0;  // shadow segments pushed (PassBufs::seg_count)
+  }
+  __syncthreads();
+  for (int base = 0; base < pb.n_tiles; base += SCAN_T) {
+    const int i = base + tid;
+    const int v = i < pb.n_tiles ? (pb.n_live[i] + EXT_BATCH - 1) / EXT_BATCH : 0;
+    int x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = wsum[lane];
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += y;
+      }
+      wsum[lane] = w;
+    }
+    __syncthreads();
+    const int excl = carry + (warp ? wsum[warp - 1] : 0) + x - v;
+    if (i < pb.n_tiles) batch_prefix[i] = excl;
+    __syncthreads();
+    if (tid == SCAN_T - 1) carry = excl + v;
+    __syncthreads();
+  }
+  if (tid == 0) batch_prefix[pb.n_tiles] = carry;
+}
+
+__global__ void __launch_bounds__(EXT_T, 6) k_extend3(const __grid_constant__ DevScene sc, const PassBufs pb, const Thr thr,
+                                                      const int* __restrict__ batch_prefix, int* __restrict__ work_ctr) {
+  __shared__ RaynHitable s_hit[RAYN_MAX_HITABLES];
+  for (int k = threadIdx.x; k < sc.n_hit; k += EXT_T) s_hit[k] = sc.hit[k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const int n_hit = sc.n_hit;
+  const float S = sc.rc.sdf_detail_scale;
+  const float c0 = 0.00005f * S, c1 = 0.05f * S;
+  const int max_marches = sc.rc.max_marches;
+  const float t_max0 = sc.rc.world_radius * 2.0f;
+  const int n_batches = batch_prefix[pb.n_tiles];
+
+  bool have = false, marching = false, exhausted = false;
+  f3 o = {0, 0, 0}, d = {0, 0, 0};
+  float closest = 0.0f, t = 0.0f;
+  int id = -1, hidx = 0, steps = 0, evals = 0, rays = 0;
+  size_t q = 0, g = 0;
+  int cur_ts = 0, cur_pos = 0, cur_end = 0;  // warp-uniform: the batch this warp is draining
+  while (true) {
+    __syncwarp();
+    unsigned idle = __ballot_sync(0xffffffffu, !have);
+    while (idle && !(exhausted && cur_pos >= cur_end)) {
+      if (cur_pos >= cur_end) {  // pull the next batch of the pass
+        int b = 0;
+        if (lane == 0) b = atomicAdd(work_ctr, 1);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= n_batches) {
+          exhausted = true;
+          break;
+        }
+        int lo = 0, hi = pb.n_tiles;  // largest ts with batch_prefix[ts] <= b
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (__ldg(batch_prefix + mid) <= b) lo = mid; else hi = mid;
+        }
+        cur_ts = lo;
+        cur_pos = (b - __ldg(batch_prefix + lo)) * EXT_BATCH;
+        cur_end = min(cur_pos + EXT_BATCH, pb.n_live[lo]);
+      }
+      const int avail = cur_end - cur_pos;
+      const int rank = __popc(idle & lt);
+      if (!have && rank < avail) {
+        q = (size_t)cur_ts * pb.R + cur_pos + rank;
+        g = (size_t)cur_ts * pb.R + pb.q_live[q];
+        const float4 o4 = pb.o_time[g], d4 = pb.d_t[g];
+        o = mk3(o4.x, o4.y, o4.z);
+        d = mk3(d4.x, d4.y, d4.z);
+        closest = t_max0;
+        id = -1;
+        hidx = 0;
+        marching = false;
+        have = true;
+        ++rays;
+      }
+      cur_pos += min(avail, __popc(idle));
+      idle = __ballot_sync(0xffffffffu, !have);
+    }
+    if (!__any_sync(0xffffffffu, have)) break;
+    if (have && !marching) {
+      while (hidx < n_hit && s_hit[hidx].kind == RAYN_HITABLE_SPHERE) {
+        const float ts_ = sphere_hit(s_hit[hidx], o, d, closest);
+        if (ts_ < closest) {
+          closest = ts_;
+          id = hidx;
+        }
+        ++hidx;
+      }
+      if (hidx >= n_hit) {
+        pb.d_t[g].w = closest;
+        pb.q_key[q] = id;
+        have = false;
+      }
+    }
+    if (have) {
+      const f3 p = marching ? fma3s(d, t, o) : o;
+      const float dd = sdf_dist(s_hit[hidx], p);
+      ++evals;
+      bool end = false;
+      if (!marching) {
+        t = dd;
+        steps = 0;
+        marching = true;
+        end = t != t;
+      } else {
+        const bool hit = dm::abs(dd) < dm::max(c0, c1 * thr.at(t));
+        const bool gt = t > closest;
+        if (hit || gt) {
+          end = true;
+        } else {
+          t = t + dd;
+          ++steps;
+          end = (t != t) || steps >= max_marches;
+        }
+      }
+      if (end) {
+        if (t < closest) {
+          closest = t;
+          id = hidx;
+        }
+        marching = false;
+        ++hidx;
+      }
+    }
+  }
+  warp_add(pb.counters + CNT_EXTEND_RAYS, rays);
+  warp_add(pb.counters + CNT_EVALS_EXTEND, evals);
+}
+
 // ---- K4/K5 v2: shade with a block-level shadow-segment pool ------------------------------------
 // Per round (surface NEE, then each volume march) every lane prepares its 4 light samples and
 // pushes the shadow segments that still need a sphere-march into a shared-memory pool; all
@@ -753,6 +918,329 @@ __global__ void __launch_bounds__(SH_T, 4) k_shade2(const __grid_constant__ DevS
   }
   warp_add(pb.counters + CNT_EVALS_SHADOW, evals);
   warp_add(pb.counters + CNT_SHADOW_RAYS, shadows);
+}
+
+// ==========================================================================================
+// v3 shading: k_shade_pre -> k_shadow (persistent) -> k_shade_post.
+// The block-level pool of k_shade2 still drains to a tail every round; v3 pushes the shadow
+// segments of the whole pass into one HBM queue and marches it with resident warps that pull
+// 32-segment batches from a global counter.  pre and post both evaluate light_contrib() - the
+// same instruction sequence on the same inputs, so the same bits - which costs a few hundred
+// cheap instructions per sample and saves storing 20 B x 12 samples per path.
+// ==========================================================================================
+struct LightContrib {
+  f3 start, end_point, c;
+  float den, trans;
+};
+// round 0: surface_sample_one_light (integrator.rs:207-240) without the visibility factor;
+// round r>0: volume_sample_one_light (:242-281) for volume march r-1.
+RT_D LightContrib light_contrib(const RaynLight& L, const RaynMaterial& mat, const ShadingPoint& sp, f3 wo, int round, float u0, float u1,
+                                float vol_sample, bool has_ext, float neg_rho_t) {
+  LightContrib r;
+  f3 li;
+  r.trans = 1.0f;
+  if (round == 0) {
+    float pdf;
+    light_sample(L, u0, u1, sp.point, &r.end_point, &li, &pdf);
+    f3 wi = r.end_point - sp.point;
+    const float dist = mag(wi);
+    wi = wi / dist;
+    r.start = sp.point + sp.normal * dm::signum(dot(sp.normal, wi)) * sp.offset_by;
+    const f3 f = bsdf_f(mat, wo, wi, sp.normal) * dm::max(dot(sp.normal, wi), 0.0f);
+    const float tr = has_ext ? dm::exp(neg_rho_t * dist) : 1.0f;
+    r.c = li * f * tr;
+    r.den = pdf;
+  } else {
+    float vol_dist, vol_pdf, light_pdf;
+    light_sample_volume(L, vol_sample, sp.o, sp.d, sp.t, &vol_dist, &vol_pdf);
+    r.start = sp.o + sp.d * vol_dist;
+    light_sample(L, u0, u1, r.start, &r.end_point, &li, &light_pdf);
+    const float dist_point_to_light = mag(r.end_point - r.start);
+    const float f = 1.0f / (4.0f * RT_PI);
+    const float tr = has_ext ? dm::exp(neg_rho_t * dist_point_to_light) : 1.0f;
+    r.c = li * f * tr;
+    r.den = vol_pdf * light_pdf;
+    r.trans = has_ext ? dm::exp(neg_rho_t * vol_dist) : 1.0f;  // :122-126
+  }
+  return r;
+}
+
+struct SlotCtx {  // what pre and post both derive for a shading slot
+  int id, sample, obj;
+  float scramble;
+  unsigned w0, w1, w2;  // light indices of the packet, one byte per packet lane, per round
+  int set1, set2;
+};
+RT_D SlotCtx slot_ctx(const DevScene& sc, const DevFrame& fr, const PassBufs& pb, int ts, int s, int nslots, int depth, int lane) {
+  SlotCtx c;
+  const int* __restrict__ qs = pb.q_shade + (size_t)ts * pb.QS;
+  c.id = s < nslots ? qs[s] : -1;
+  c.sample = 0;
+  c.scramble = 0.0f;  // padded lanes are Ray::new_invalid: sample 0, scramble 0 (ray.rs:54-66)
+  if (c.id >= 0) {
+    const TileGeom tg = tile_geom(fr, pb.tile_ids[ts]);
+    const int pl = c.id / fr.spp;
+    c.sample = c.id - pl * fr.spp;
+    const int xl = pl / tg.th, yl = pl - xl * tg.th;
+    c.scramble = __ldg(fr.scramble + (tg.x0 + xl) + (size_t)(tg.y0 + yl) * fr.W);
+  }
+  const int n1 = 3 + fr.vm, n2h = (12 + 8 * fr.vm) / 2;
+  c.set1 = 1 + depth * n1;
+  c.set2 = 2 + depth * n2h;
+  const int nl = sc.n_lights;
+  unsigned pack = 0;
+  if (nl > 0)
+    pack = (unsigned)light_index(samp1(fr, c.sample, c.scramble, c.set1 + 0), nl) |
+           ((unsigned)light_index(samp1(fr, c.sample, c.scramble, c.set1 + 1), nl) << 8) |
+           ((unsigned)light_index(samp1(fr, c.sample, c.scramble, c.set1 + 2), nl) << 16);
+  c.w0 = c.w1 = c.w2 = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const unsigned pk = __shfl_sync(0xffffffffu, pack, (lane & ~3) + k);
+    c.w0 |= (pk & 0xffu) << (8 * k);
+    c.w1 |= ((pk >> 8) & 0xffu) << (8 * k);
+    c.w2 |= ((pk >> 16) & 0xffu) << (8 * k);
+  }
+  c.obj = 0;
+  if (c.id >= 0) {
+    const int* __restrict__ bs = pb.bin_start + ts * (RAYN_MAX_HITABLES + 1);
+    while (c.obj + 1 < sc.n_hit && s >= bs[c.obj + 1]) ++c.obj;
+  }
+  return c;
+}
+
+__global__ void __launch_bounds__(128, 4) k_shade_pre(const __grid_constant__ DevScene sc, const DevFrame fr, const PassBufs pb,
+                                                      const int depth, const Thr thr) {
+  const int ts = blockIdx.y;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nslots = pb.n_slots[ts];
+  if ((s & ~31) >= nslots) return;  // warp-uniform
+  const SlotCtx cx = slot_ctx(sc, fr, pb, ts, s, nslots, depth, threadIdx.x & 31);
+  const bool valid = cx.id >= 0;
+  warp_add(pb.counters + CNT_SHADE_LANES, valid ? 1 : 0);
+  int evals = 0, shadows = 0;
+  if (valid) {
+    const RaynHitable& h = sc.hit[cx.obj];
+    const RaynMaterial& mat = sc.mat[h.material];
+    const size_t g = (size_t)ts * pb.R + cx.id;
+    const float4 o4 = pb.o_time[g], d4 = pb.d_t[g], r4 = pb.rad[g], t4 = pb.thr[g];
+    ShadingPoint sp;
+    sp.o = mk3(o4.x, o4.y, o4.z);
+    sp.d = mk3(d4.x, d4.y, d4.z);
+    sp.time = o4.w;
+    sp.t = d4.w;
+    shading_info(sc, h, thr, sp, &evals);
+    pb.nrm[g] = make_float4(sp.normal.x, sp.normal.y, sp.normal.z, sp.offset_by);
+    const f3 wo = -sp.d;
+    const bool has_ext = sc.vol.has_extinction != 0;
+    const float neg_rho_t = -sc.vol.coeff_extinction;
+    const float vt = has_ext ? dm::exp(neg_rho_t * sp.t) : 1.0f;                          // integrator.rs:64-68
+    const f3 radiance = mk3(r4.x, r4.y, r4.z) + bsdf_le(mat, wo) * mk3(t4.x, t4.y, t4.z) * vt;  // :70-71
+    pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+    const bool recv = receives_light(mat);
+    const int nl = sc.n_lights;
+    const bool scat = sc.vol.has_scattering != 0 && nl > 0;
+    const int n_rounds = nl > 0 ? 1 + (scat ? fr.vm : 0) : 0;
+    unsigned vis = 0xffffffffu;
+    for (int round = (recv ? 0 : 1); round < n_rounds; ++round) {
+      const unsigned wr = round == 0 ? cx.w0 : (round == 1 ? cx.w1 : cx.w2);
+      const float vol_sample = round == 0 ? 0.0f : samp1(fr, cx.sample, cx.scramble, cx.set1 + 1);  // samples_1d[1], :115
+#pragma unroll 1
+      for (int i = 0; i < 4; ++i) {
+        const int set = round == 0 ? cx.set2 + i : cx.set2 + 4 + 4 * (round - 1) + i;
+        const LightContrib lc = light_contrib(sc.light[(wr >> (8 * i)) & 0xffu], mat, sp, wo, round, samp2(fr, 0, cx.sample, cx.scramble, set),
+                                              samp2(fr, 1, cx.sample, cx.scramble, set), vol_sample, has_ext, neg_rho_t);
+        ++shadows;
+        const int bit = round * 4 + i;
+        // a contribution that is (+-0 | NaN) in every channel is the same bits for visibility 0 and 1
+        const bool irrelevant = (lc.c.x == 0.0f || lc.c.x != lc.c.x) && (lc.c.y == 0.0f || lc.c.y != lc.c.y) && (lc.c.z == 0.0f || lc.c.z != lc.c.z);
+        if (irrelevant) continue;
+        float v = 1.0f;  // analytic spheres first: product of {0,1} factors (hitable.rs:164-168)
+        for (int k = 0; k < sc.n_hit && v != 0.0f; ++k)
+          if (sc.hit[k].kind == RAYN_HITABLE_SPHERE) v = sphere_occluded(sc.hit[k], lc.start, lc.end_point);
+        if (v == 0.0f) {
+          vis &= ~(1u << bit);
+          continue;
+        }
+        f3 dir = lc.end_point - lc.start;  // TracedSDF::occluded prologue, sdf.rs:26-28
+        const float max_dist = mag(dir);
+        dir = dir / max_dist;
+        for (int k = 0; k < sc.n_hit; ++k)
+          if (sc.hit[k].kind != RAYN_HITABLE_SPHERE) {
+            const unsigned am = __activemask();  // opportunistic warp aggregation of the queue append
+            const int leader = __ffs(am) - 1, ln = threadIdx.x & 31;
+            int base = 0;
+            if (ln == leader) base = atomicAdd(pb.seg_count, __popc(am));
+            base = __shfl_sync(am, base, leader);
+            const int slot = base + __popc(am & ((1u << ln) - 1u));
+            pb.seg_a[slot] = make_float4(lc.start.x, lc.start.y, lc.start.z, max_dist);
+            pb.seg_b[slot] = make_float4(dir.x, dir.y, dir.z, __int_as_float(bit | (k << 8)));
+            pb.seg_owner[slot] = (int)g;
+          }
+      }
+    }
+    pb.vis[g] = vis;
+  }
+  warp_add(pb.counters + CNT_EVALS_SHADOW, evals);
+  warp_add(pb.counters + CNT_SHADOW_RAYS, shadows);
+}
+
+// K5: persistent shadow sphere-march over the pass-wide segment queue.
+// TracedSDF::occluded per lane (sdf.rs:25-57); occlusion clears the owner's bit.
+#define SHD_T 128
+__global__ void __launch_bounds__(SHD_T, 8) k_shadow(const __grid_constant__ DevScene sc, const PassBufs pb, int* __restrict__ work_ctr) {
+  __shared__ RaynHitable s_hit[RAYN_MAX_HITABLES];
+  for (int k = threadIdx.x; k < sc.n_hit; k += SHD_T) s_hit[k] = sc.hit[k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const int n_seg = *pb.seg_count;
+  const float S = sc.rc.sdf_detail_scale;
+  const float oc0 = 0.0001f * S, oc1 = 0.00001f * S;
+  const int max_vis = sc.rc.max_vis_marches;
+  bool have = false, first = false, exhausted = false;
+  f3 st = {0, 0, 0}, dir = {0, 0, 0};
+  float max_dist = 0.0f, t = 0.0f;
+  int owner = 0, bit = 0, hk = 0, steps = 0, evals = 0;
+  int cur_pos = 0, cur_end = 0;
+  while (true) {
+    __syncwarp();
+    unsigned idle = __ballot_sync(0xffffffffu, !have);
+    while (idle && !(exhausted && cur_pos >= cur_end)) {
+      if (cur_pos >= cur_end) {
+        int b = 0;
+        if (lane == 0) b = atomicAdd(work_ctr, 64);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= n_seg) {
+          exhausted = true;
+          break;
+        }
+        cur_pos = b;
+        cur_end = min(b + 64, n_seg);
+      }
+      const int avail = cur_end - cur_pos;
+      const int rank = __popc(idle & lt);
+      if (!have && rank < avail) {
+        const int idx = cur_pos + rank;
+        const float4 a = pb.seg_a[idx], b4 = pb.seg_b[idx];
+        st = mk3(a.x, a.y, a.z);
+        max_dist = a.w;
+        dir = mk3(b4.x, b4.y, b4.z);
+        const int ow = __float_as_int(b4.w);
+        bit = ow & 0xff;
+        hk = ow >> 8;
+        owner = pb.seg_owner[idx];
+        first = true;
+        have = true;
+      }
+      cur_pos += min(avail, __popc(idle));
+      idle = __ballot_sync(0xffffffffu, !have);
+    }
+    if (!__any_sync(0xffffffffu, have)) break;
+    if (have) {
+      const f3 p = first ? st : fma3s(dir, t, st);
+      const float dd = sdf_dist(s_hit[hk], p);
+      ++evals;
+      bool done = false;
+      if (first) {
+        t = dd;
+        first = false;
+        steps = 0;
+        done = (t != t) || (t > max_dist);
+      } else if (dm::abs(dd) < dm::max(oc0, oc1 * t)) {
+        atomicAnd(pb.vis + owner, ~(1u << bit));  // occluded
+        done = true;
+      } else {
+        t = t + dd;
+        ++steps;
+        done = (t != t) || steps >= max_vis || (t > max_dist);
+      }
+      if (done) have = false;
+    }
+  }
+  warp_add(pb.counters + CNT_EVALS_SHADOW, evals);
+}
+
+__global__ void __launch_bounds__(128, 4) k_shade_post(const __grid_constant__ DevScene sc, const DevFrame fr, const PassBufs pb,
+                                                       const int depth) {
+  const int ts = blockIdx.y;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nslots = pb.n_slots[ts];
+  if ((s & ~31) >= nslots) return;
+  const SlotCtx cx = slot_ctx(sc, fr, pb, ts, s, nslots, depth, threadIdx.x & 31);
+  if (cx.id < 0) return;
+  int* __restrict__ qs = pb.q_shade + (size_t)ts * pb.QS;
+  const RaynHitable& h = sc.hit[cx.obj];
+  const RaynMaterial& mat = sc.mat[h.material];
+  const size_t g = (size_t)ts * pb.R + cx.id;
+  const float4 o4 = pb.o_time[g], d4 = pb.d_t[g], r4 = pb.rad[g], t4 = pb.thr[g], n4 = pb.nrm[g];
+  ShadingPoint sp;
+  sp.o = mk3(o4.x, o4.y, o4.z);
+  sp.d = mk3(d4.x, d4.y, d4.z);
+  sp.time = o4.w;
+  sp.t = d4.w;
+  sp.point = fma3s(sp.d, sp.t, sp.o);
+  sp.normal = mk3(n4.x, n4.y, n4.z);
+  sp.offset_by = n4.w;
+  sp.basis = onb(sp.normal);
+  f3 radiance = mk3(r4.x, r4.y, r4.z), throughput = mk3(t4.x, t4.y, t4.z);
+  const f3 wo = -sp.d;
+  const bool has_ext = sc.vol.has_extinction != 0;
+  const float neg_rho_t = -sc.vol.coeff_extinction;
+  const float vt = has_ext ? dm::exp(neg_rho_t * sp.t) : 1.0f;
+  const bool recv = receives_light(mat);
+  const int nl = sc.n_lights;
+  const bool scat = sc.vol.has_scattering != 0 && nl > 0;
+  const int n_rounds = nl > 0 ? 1 + (scat ? fr.vm : 0) : 0;
+  const unsigned vis = pb.vis[g];
+  for (int round = (recv ? 0 : 1); round < n_rounds; ++round) {
+    const unsigned wr = round == 0 ? cx.w0 : (round == 1 ? cx.w1 : cx.w2);
+    const float vol_sample = round == 0 ? 0.0f : samp1(fr, cx.sample, cx.scramble, cx.set1 + 1);
+    const float correction = round == 0 ? (float)nl / 4.0f : (float)nl / 4.0f / (float)fr.vm;  // :79-80,104-108
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+      const int set = round == 0 ? cx.set2 + i : cx.set2 + 4 + 4 * (round - 1) + i;
+      const LightContrib lc = light_contrib(sc.light[(wr >> (8 * i)) & 0xffu], mat, sp, wo, round, samp2(fr, 0, cx.sample, cx.scramble, set),
+                                            samp2(fr, 1, cx.sample, cx.scramble, set), vol_sample, has_ext, neg_rho_t);
+      const float occluded = (vis >> (round * 4 + i)) & 1u ? 1.0f : 0.0f;
+      const f3 contrib = lc.c * occluded / lc.den;
+      if (round == 0)
+        radiance = radiance + contrib * throughput * correction * vt;  // :91-92
+      else
+        radiance = radiance + contrib * throughput * correction * sc.vol.coeff_scattering * lc.trans;  // :128-129
+    }
+  }
+  if (recv) {  // :134-188
+    const int setb = cx.set2 + 4 + 4 * fr.vm;
+    const Scatter se = bsdf_scatter(mat, wo, sp, samp1(fr, cx.sample, cx.scramble, cx.set1 + 3), samp2(fr, 0, cx.sample, cx.scramble, setb),
+                                    samp2(fr, 1, cx.sample, cx.scramble, setb), samp2(fr, 0, cx.sample, cx.scramble, setb + 1),
+                                    samp2(fr, 1, cx.sample, cx.scramble, setb + 1));
+    const float ndl = dm::abs(dot(se.wi, sp.normal));
+    f3 new_throughput = throughput * vt * se.f * ndl / se.pdf;
+    float roulette_factor = 0.0f;
+    if (depth > 2) {
+      roulette_factor = dm::max(1.0f - component_max(throughput), 0.05f);
+      new_throughput = new_throughput / (1.0f - roulette_factor);
+    }
+    if (depth == 0) pb.nrm0[g] = make_float4(sp.normal.x, sp.normal.y, sp.normal.z, __uint_as_float((unsigned)s + 1u));
+    const float roulette_sample = samp1(fr, cx.sample, cx.scramble, cx.set1 + 4);
+    if (depth >= fr.max_bounces || roulette_sample < roulette_factor) {
+      pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+      pb.term[g] = (TERM_COLOR << 30) | ((unsigned)depth << 20) | (unsigned)s;
+      qs[s] = -1;
+    } else {
+      const f3 no = sp.point + sp.normal * dm::signum(dot(sp.normal, se.wi)) * sp.offset_by;
+      if (!any_nan(new_throughput)) throughput = new_throughput;
+      pb.o_time[g] = make_float4(no.x, no.y, no.z, sp.time);
+      pb.d_t[g] = make_float4(se.wi.x, se.wi.y, se.wi.z, 0.0f);
+      pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+      pb.thr[g] = make_float4(throughput.x, throughput.y, throughput.z, 0.0f);
+    }
+  } else {  // :189-203
+    pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+    pb.term[g] = ((depth == 0 ? TERM_BACKGROUND : TERM_COLOR) << 30) | ((unsigned)depth << 20) | (unsigned)s;
+    qs[s] = -1;
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -267,17 +267,19 @@ def test_gpu_matches_committed_golden(renderer):
             assert_bit_equal(g[ch], gold[ch], f"golden {name} {ch}")
 
 
-def test_simple_march_kernels_stay_bit_exact(oracle):
-    """RAYN_FLAG_SIMPLE_MARCH selects the one-thread-per-ray v0 kernels (no lane refill, no
-    shadow pool); both kernel families must give the oracle's bits."""
+def test_alternative_kernel_families_stay_bit_exact(oracle):
+    """RAYN_FLAG_SIMPLE_MARCH = v0 one-thread-per-ray kernels, RAYN_FLAG_BLOCK_POOL = v2 per-block
+    refill / shadow pool; the default is v3 (pass-wide persistent march kernels).  All three
+    families must give the oracle's bits."""
     for n, res, samples, mb in [(3, (48, 48), 2, 4), (4, (32, 32), 1, 2)]:
         c, inp = small_config(n, res, samples, mb)
         o, _ = oracle.render(c["world"], c["camera"], inp, (16, 16), c["integrator"], TR)
-        r = Renderer(0, flags=L.FLAG_SIMPLE_MARCH)
-        try:
-            r.upload_scene(c["world"], c["camera"])
-            g = r.render_host(inp, (16, 16), c["integrator"], TR)
-        finally:
-            r.close()
-        for ch in CH:
-            assert_bit_equal(g[ch], o[ch], f"simple-march cfg{n} {ch}")
+        for flag in (L.FLAG_SIMPLE_MARCH, L.FLAG_BLOCK_POOL):
+            r = Renderer(0, flags=flag)
+            try:
+                r.upload_scene(c["world"], c["camera"])
+                g = r.render_host(inp, (16, 16), c["integrator"], TR)
+            finally:
+                r.close()
+            for ch in CH:
+                assert_bit_equal(g[ch], o[ch], f"kernel family {flag} cfg{n} {ch}")
