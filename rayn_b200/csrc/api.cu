@@ -397,7 +397,25 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
         k_scan_live<<<1, SCAN_T, 0, st>>>(pb, ctx->d_batch_prefix, ctx->d_work_ctr);
         ctx->stats.launches++;
         ctx->stats.kernel_launches[RAYN_K_MISC]++;
-        k_extend3<<<ctx->n_sm * 8, EXT_T, 0, st>>>(ctx->scene, pb, thr, ctx->d_batch_prefix, ctx->d_work_ctr);
+        // fold order of hitable.rs:177-198: runs of spheres as coherent kernels, each SDF as a persistent march
+        int k = 0, first_kernel = 1, n_march = 0;
+        while (k < n_hit || first_kernel) {
+          int e = k;
+          while (e < n_hit && ctx->scene.hit[e].kind == RAYN_HITABLE_SPHERE) ++e;
+          if (e > k || first_kernel) {
+            k_extend_spheres<<<g_paths, 256, 0, st>>>(ctx->scene, pb, k, e, first_kernel);
+            ctx->stats.launches++;
+            first_kernel = 0;
+          }
+          if (e < n_hit) {
+            if (n_march++ > 0) CU(cudaMemsetAsync(ctx->d_work_ctr, 0, sizeof(int), st));
+            k_extend_march<<<ctx->n_sm * 8, EXT_T, 0, st>>>(ctx->scene, pb, thr, e, ctx->d_batch_prefix, ctx->d_work_ctr);
+            ctx->stats.launches++;
+            ++e;
+          }
+          k = e;
+        }
+        ctx->stats.launches--;  // timed_end below counts one launch of this group
       }
       timed_end(ctx, RAYN_K_EXTEND);
       timed_begin(ctx, RAYN_K_BIN);

@@ -642,6 +642,128 @@ __global__ void __launch_bounds__(EXT_T, 6) k_extend3(const __grid_constant__ De
   warp_add(pb.counters + CNT_EVALS_EXTEND, evals);
 }
 
+// ---- K2 v4: closest hit split by hitable kind.  ncu on k_extend3 (profiles/r01 notes): the
+// per-ray prologue/epilogue (sphere tests, gathers, stores) ran at 1-4 active lanes inside the
+// persistent loop and cost more issue slots than the marches of cheap (sky) rays.  v4 keeps the
+// fold order of hitable.rs:177-198 but runs every maximal run of analytic spheres as a coherent
+// one-thread-per-ray kernel and every SDF hitable as a pure persistent march kernel.
+__global__ void __launch_bounds__(256) k_extend_spheres(const __grid_constant__ DevScene sc, const PassBufs pb, const int first,
+                                                        const int last, const int init) {
+  const int ts = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = pb.n_live[ts];
+  if ((i & ~31) >= n) return;  // warp-uniform
+  const bool act = i < n;
+  if (act) {
+    const size_t q = (size_t)ts * pb.R + i;
+    const size_t g = (size_t)ts * pb.R + pb.q_live[q];
+    const float4 o4 = pb.o_time[g], d4 = pb.d_t[g];
+    const f3 o = mk3(o4.x, o4.y, o4.z), d = mk3(d4.x, d4.y, d4.z);
+    float closest = init ? sc.rc.world_radius * 2.0f : d4.w;  // film.rs:556
+    int id = init ? -1 : pb.q_key[q];
+    for (int k = first; k < last; ++k) {
+      const float t = sphere_hit(sc.hit[k], o, d, closest);
+      if (t < closest) {
+        closest = t;
+        id = k;
+      }
+    }
+    pb.d_t[g].w = closest;
+    pb.q_key[q] = id;
+  }
+  if (init) warp_add(pb.counters + CNT_EXTEND_RAYS, act ? 1 : 0);
+}
+
+// TracedSDF::hit (sdf.rs:59-83) for hitable `hk` over every live ray of the pass.
+__global__ void __launch_bounds__(EXT_T, 8) k_extend_march(const __grid_constant__ DevScene sc, const PassBufs pb, const Thr thr,
+                                                           const int hk, const int* __restrict__ batch_prefix, int* __restrict__ work_ctr) {
+  __shared__ RaynHitable s_h;  // shared-memory staging of the fractal constants
+  if (threadIdx.x == 0) s_h = sc.hit[hk];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const float S = sc.rc.sdf_detail_scale;
+  const float c0 = 0.00005f * S, c1 = 0.05f * S;
+  const int max_marches = sc.rc.max_marches;
+  const int n_batches = batch_prefix[pb.n_tiles];
+  bool have = false, first = false, exhausted = false;
+  f3 o = {0, 0, 0}, d = {0, 0, 0};
+  float closest = 0.0f, t = 0.0f;
+  int steps = 0, evals = 0, rays = 0;
+  size_t q = 0, g = 0;
+  int cur_ts = 0, cur_pos = 0, cur_end = 0;
+  while (true) {
+    __syncwarp();
+    unsigned idle = __ballot_sync(0xffffffffu, !have);
+    while (idle && !(exhausted && cur_pos >= cur_end)) {
+      if (cur_pos >= cur_end) {
+        int b = 0;
+        if (lane == 0) b = atomicAdd(work_ctr, 1);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= n_batches) {
+          exhausted = true;
+          break;
+        }
+        int lo = 0, hi = pb.n_tiles;
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if (__ldg(batch_prefix + mid) <= b) lo = mid; else hi = mid;
+        }
+        cur_ts = lo;
+        cur_pos = (b - __ldg(batch_prefix + lo)) * EXT_BATCH;
+        cur_end = min(cur_pos + EXT_BATCH, pb.n_live[lo]);
+      }
+      const int avail = cur_end - cur_pos;
+      const int rank = __popc(idle & lt);
+      if (!have && rank < avail) {
+        q = (size_t)cur_ts * pb.R + cur_pos + rank;
+        g = (size_t)cur_ts * pb.R + pb.q_live[q];
+        const float4 o4 = pb.o_time[g], d4 = pb.d_t[g];
+        o = mk3(o4.x, o4.y, o4.z);
+        d = mk3(d4.x, d4.y, d4.z);
+        closest = d4.w;
+        first = true;
+        have = true;
+        ++rays;
+      }
+      cur_pos += min(avail, __popc(idle));
+      idle = __ballot_sync(0xffffffffu, !have);
+    }
+    if (!__any_sync(0xffffffffu, have)) break;
+    if (have) {
+      const f3 p = first ? o : fma3s(d, t, o);
+      const float dd = sdf_dist(s_h, p);
+      ++evals;
+      bool end = false;
+      if (first) {
+        t = dd;
+        steps = 0;
+        first = false;
+        end = t != t;
+      } else {
+        const bool hit = dm::abs(dd) < dm::max(c0, c1 * thr.at(t));
+        const bool gt = t > closest;
+        if (hit || gt) {
+          end = true;
+        } else {
+          t = t + dd;
+          ++steps;
+          end = (t != t) || steps >= max_marches;
+        }
+      }
+      if (end) {
+        if (t < closest) {  // hitable.rs:190-193
+          pb.d_t[g].w = t;
+          pb.q_key[q] = hk;
+        }
+        have = false;
+      }
+    }
+  }
+  (void)rays;
+  warp_add(pb.counters + CNT_EVALS_EXTEND, evals);
+}
+
 // ---- K4/K5 v2: shade with a block-level shadow-segment pool ------------------------------------
 // Per round (surface NEE, then each volume march) every lane prepares its 4 light samples and
 // pushes the shadow segments that still need a sphere-march into a shared-memory pool; all
