@@ -195,6 +195,9 @@ typedef struct RaynConfig {
 #define RAYN_FLAG_BLOCK_POOL 4   /* v2: per-block refill / shadow pool instead of the
                                     pass-wide persistent march kernels (v3, default)       */
 
+#define RAYN_FLAG_FLATTEN 8      /* experimental: iteration-granular march trips for the Mandelbulb
+                                    (measured slower than evaluation-granular trips; off by default) */
+
 #define RAYN_STAT_KERNELS 12
 typedef struct RaynStats {
   int64_t launches;                 /* kernels launched by the last render call            */

@@ -424,7 +424,7 @@ inline F4 mandelbulb_dist(const RaynHitable& h, V3 p) {
     m = merge(esc, m, nm);
   }
   F4 r = f4sqrt(m);
-  F4 lnr = map4(r, [](float x) { return dm::ln(x); });
+  F4 lnr = map4(r, [](float x) { return dm::ln_fast(x); });
   return splat(0.5f) * lnr * r / dr;
 }
 

@@ -27,7 +27,7 @@ HITABLE_SPHERE, HITABLE_MANDELBOX, HITABLE_MANDELBULB = 0, 1, 2
 MATERIAL_LAMBERTIAN, MATERIAL_DIELECTRIC, MATERIAL_SKY, MATERIAL_EMISSIVE = 0, 1, 2, 3
 CAMERA_PINHOLE, CAMERA_THINLENS, CAMERA_ORTHOGRAPHIC = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
-FLAG_TIMING, FLAG_SIMPLE_MARCH, FLAG_BLOCK_POOL = 1, 2, 4
+FLAG_TIMING, FLAG_SIMPLE_MARCH, FLAG_BLOCK_POOL, FLAG_FLATTEN = 1, 2, 4, 8
 STAT_KERNELS = 12
 KERNEL_NAMES = ["raygen", "extend", "bin", "shade_pre", "shadow", "shade_post", "compact", "resolve", "misc"]
 

@@ -362,6 +362,9 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
   const bool simple = (ctx->flags & RAYN_FLAG_SIMPLE_MARCH) != 0;
   const bool block_pool = !simple && (ctx->flags & RAYN_FLAG_BLOCK_POOL) != 0 && n_sdf <= SH_MAX_SDF;
   const bool v3 = !simple && !block_pool;
+  const bool no_flat = (ctx->flags & RAYN_FLAG_FLATTEN) == 0;
+  bool any_bulb = false;
+  for (int i = 0; i < n_hit; ++i) any_bulb |= ctx->scene.hit[i].kind == RAYN_HITABLE_MANDELBULB;
   const bool volume_on = ctx->scene.vol.has_scattering != 0 && ctx->scene.n_lights > 0;
   const int seg_per_path = v3 ? (volume_on ? 4 * (1 + vm) : 4) * n_sdf : 0;  // worst case shadow segments per path per depth
   if (v3 && volume_on) tiles_per_pass = std::max(1, tiles_per_pass / 3);
@@ -409,7 +412,10 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
           }
           if (e < n_hit) {
             if (n_march++ > 0) CU(cudaMemsetAsync(ctx->d_work_ctr, 0, sizeof(int), st));
-            k_extend_march<<<ctx->n_sm * 8, EXT_T, 0, st>>>(ctx->scene, pb, thr, e, ctx->d_batch_prefix, ctx->d_work_ctr);
+            if (ctx->scene.hit[e].kind == RAYN_HITABLE_MANDELBULB && !no_flat)
+              k_extend_march<true><<<ctx->n_sm * 8, EXT_T, 0, st>>>(ctx->scene, pb, thr, e, ctx->d_batch_prefix, ctx->d_work_ctr);
+            else
+              k_extend_march<false><<<ctx->n_sm * 8, EXT_T, 0, st>>>(ctx->scene, pb, thr, e, ctx->d_batch_prefix, ctx->d_work_ctr);
             ctx->stats.launches++;
             ++e;
           }
@@ -440,7 +446,10 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
         timed_end(ctx, RAYN_K_SHADE_PRE);
         if (n_sdf > 0 && ctx->scene.n_lights > 0) {
           timed_begin(ctx, RAYN_K_SHADOW);
-          k_shadow<<<ctx->n_sm * 8, SHD_T, 0, st>>>(ctx->scene, pb, ctx->d_work_ctr + 1);
+          if (any_bulb && !no_flat)
+            k_shadow<true><<<ctx->n_sm * 8, SHD_T, 0, st>>>(ctx->scene, pb, ctx->d_work_ctr + 1);
+          else
+            k_shadow<false><<<ctx->n_sm * 8, SHD_T, 0, st>>>(ctx->scene, pb, ctx->d_work_ctr + 1);
           timed_end(ctx, RAYN_K_SHADOW);
         }
         timed_begin(ctx, RAYN_K_SHADE_POST);

@@ -134,65 +134,81 @@ __host__ __device__ inline Thr make_thr(const RaynCamera& cam, int depth) {
 }
 
 // ---- SDFs ----------------------------------------------------------------------------------
-// MandelBox::dist, sdf.rs:125-141 (+ BoxFold :160-162, SphereFold :181-187)
-RT_D float mandelbox_dist(const RaynHitable& h, f3 p) {
-  const f3 offset = p;
-  float dr = 1.0f;
-  const float l = h.box_l, nl = -h.box_l, scale = h.scale;
-  const float min_rad_sq = h.min_rad_sq, fixed_rad_sq = h.fixed_rad_sq;
-  for (int i = 0; i < h.iterations; ++i) {
+// A distance evaluation is kept as an explicit little state machine (start / more / step /
+// finish) so that the eval-granular kernels and the iteration-granular ("flattened") march
+// kernels execute literally the same arithmetic.
+//   MandelBox::dist, sdf.rs:125-141 (+ BoxFold :160-162, SphereFold :181-187):
+//     w = running point, c = offset (the original point), dr, it.
+//   Mandelbulb (AUTHORED, no reference counterpart; definition in DESIGN.md):
+//     w, c, dr, m = |w|^2, it; stops early once m > bailout^2.
+struct SdfEval {
+  f3 w, c;
+  float dr, m;
+  int it;
+};
+RT_D void eval_start(SdfEval& e, const RaynHitable& h, f3 p) {
+  e.w = p;
+  e.c = p;
+  e.dr = 1.0f;
+  e.it = 0;
+  e.m = h.kind == RAYN_HITABLE_MANDELBULB ? dot(p, p) : 0.0f;
+}
+RT_D bool eval_more(const SdfEval& e, const RaynHitable& h) {
+  if (h.kind == RAYN_HITABLE_MANDELBULB) return e.it < h.iterations && !(e.m > h.bulb_bailout * h.bulb_bailout);
+  return e.it < h.iterations;
+}
+RT_D void eval_step(SdfEval& e, const RaynHitable& h) {
+  if (h.kind == RAYN_HITABLE_MANDELBULB) {
+    const f3 w = e.w;
+    const float m = e.m;
+    const float m2 = m * m, m3 = m2 * m;
+    const float r = sqrtf(m);
+    const float r7 = m3 * r;
+    e.dr = dm::fma(8.0f * r7, e.dr, 1.0f);
+    const float a = w.z * w.z, b = m;
+    const float b2 = b * b, b3 = b2 * b, b4 = b2 * b2;
+    const float P = (((128.0f * a - 256.0f * b) * a + 160.0f * b2) * a - 32.0f * b3) * a + b4;
+    const float A = ((128.0f * a - 192.0f * b) * a + 80.0f * b2) * a - 8.0f * b3;
+    const float ax = w.x * w.x;
+    const float q = dm::fma(w.x, w.x, w.y * w.y);
+    const float q2 = q * q, q3 = q2 * q, q4 = q2 * q2;
+    const float C = (((128.0f * ax - 256.0f * q) * ax + 160.0f * q2) * ax - 32.0f * q3) * ax + q4;
+    const float B = ((128.0f * ax - 192.0f * q) * ax + 80.0f * q2) * ax - 8.0f * q3;
+    float k = (w.z * A) / (q3 * sqrtf(q));
+    k = q > 0.0f ? k : 0.0f;
+    e.w = mk3(k * C + e.c.x, k * (w.x * w.y * B) + e.c.y, P + e.c.z);
+    e.m = dot(e.w, e.w);
+  } else {
+    const float l = h.box_l, nl = -h.box_l;
+    f3 p = e.w;
     // clamped(neg_l, l) = max(neg_l).min(l), then mul_add(two, -p)
-    float cx = dm::min(dm::max(p.x, nl), l);
-    float cy = dm::min(dm::max(p.y, nl), l);
-    float cz = dm::min(dm::max(p.z, nl), l);
+    const float cx = dm::min(dm::max(p.x, nl), l);
+    const float cy = dm::min(dm::max(p.y, nl), l);
+    const float cz = dm::min(dm::max(p.z, nl), l);
     p.x = dm::fma(cx, 2.0f, -p.x);
     p.y = dm::fma(cy, 2.0f, -p.y);
     p.z = dm::fma(cz, 2.0f, -p.z);
-    float r2 = mag_sq(p);
-    float mul = dm::max(1.0f, fixed_rad_sq / dm::max(min_rad_sq, r2));
+    const float r2 = mag_sq(p);
+    const float mul = dm::max(1.0f, h.fixed_rad_sq / dm::max(h.min_rad_sq, r2));
     p = p * mul;
-    dr = dr * mul;
-    p = fma3s(p, scale, offset);
-    dr = dm::fma(-dr, scale, 1.0f);
+    e.dr = e.dr * mul;
+    e.w = fma3s(p, h.scale, e.c);
+    e.dr = dm::fma(-e.dr, h.scale, 1.0f);
   }
-  return mag(p) / dm::abs(dr);
+  ++e.it;
 }
-
-// AUTHORED power-8 Mandelbulb (no reference counterpart).  Definition in
-// DESIGN.md §"Mandelbulb"; must match oracle/rayn_oracle.cpp::mandelbulb_dist bit for bit.
-RT_D float mandelbulb_dist(const RaynHitable& h, f3 p) {
-  f3 w = p;
-  float dr = 1.0f;
-  float m = dot(w, w);
-  const float bail2 = h.bulb_bailout * h.bulb_bailout;
-  for (int i = 0; i < h.iterations; ++i) {
-    if (m > bail2) break;
-    float m2 = m * m, m3 = m2 * m;
-    float r = sqrtf(m);
-    float r7 = m3 * r;
-    dr = dm::fma(8.0f * r7, dr, 1.0f);
-    float a = w.z * w.z, b = m;
-    float b2 = b * b, b3 = b2 * b, b4 = b2 * b2;
-    float P = (((128.0f * a - 256.0f * b) * a + 160.0f * b2) * a - 32.0f * b3) * a + b4;
-    float A = ((128.0f * a - 192.0f * b) * a + 80.0f * b2) * a - 8.0f * b3;
-    float ax = w.x * w.x;
-    float q = dm::fma(w.x, w.x, w.y * w.y);
-    float q2 = q * q, q3 = q2 * q, q4 = q2 * q2;
-    float C = (((128.0f * ax - 256.0f * q) * ax + 160.0f * q2) * ax - 32.0f * q3) * ax + q4;
-    float B = ((128.0f * ax - 192.0f * q) * ax + 80.0f * q2) * ax - 8.0f * q3;
-    float k = (w.z * A) / (q3 * sqrtf(q));
-    k = q > 0.0f ? k : 0.0f;
-    f3 nw = {k * C + p.x, k * (w.x * w.y * B) + p.y, P + p.z};
-    w = nw;
-    m = dot(w, w);
+RT_D float eval_finish(const SdfEval& e, const RaynHitable& h) {
+  if (h.kind == RAYN_HITABLE_MANDELBULB) {
+    const float r = sqrtf(e.m);
+    return 0.5f * dm::ln_fast(r) * r / e.dr;
   }
-  float r = sqrtf(m);
-  return 0.5f * dm::ln(r) * r / dr;
+  return mag(e.w) / dm::abs(e.dr);
 }
-
 RT_D float sdf_dist(const RaynHitable& h, f3 p) {
-  if (h.kind == RAYN_HITABLE_MANDELBULB) return mandelbulb_dist(h, p);
-  return mandelbox_dist(h, p);
+  SdfEval e;
+  eval_start(e, h, p);
+  while (eval_more(e, h)) eval_step(e, h);
+  return eval_finish(e, h);
 }
 
 // TracedSDF::hit per lane, sdf.rs:59-83 / SURVEY §9.1.  *evals counts dist() calls.

@@ -675,6 +675,12 @@ __global__ void __launch_bounds__(256) k_extend_spheres(const __grid_constant__ 
 }
 
 // TracedSDF::hit (sdf.rs:59-83) for hitable `hk` over every live ray of the pass.
+// FLAT = iteration-granular trips: one loop trip is ONE fractal iteration on every busy lane; a
+// lane whose evaluation completes runs the short epilogue (distance estimate, hit test, step)
+// in the same trip.  Used when the SDF is the Mandelbulb, whose per-evaluation iteration count
+// varies from 0 to `iterations` (ncu r1v3: 12-14 of 32 lanes active inside the iteration body
+// with evaluation-granular trips).  The arithmetic is the same SdfEval state machine either way.
+template <bool FLAT>
 __global__ void __launch_bounds__(EXT_T, 8) k_extend_march(const __grid_constant__ DevScene sc, const PassBufs pb, const Thr thr,
                                                            const int hk, const int* __restrict__ batch_prefix, int* __restrict__ work_ctr) {
   __shared__ RaynHitable s_h;  // shared-memory staging of the fractal constants
@@ -692,6 +698,10 @@ __global__ void __launch_bounds__(EXT_T, 8) k_extend_march(const __grid_constant
   int steps = 0, evals = 0, rays = 0;
   size_t q = 0, g = 0;
   int cur_ts = 0, cur_pos = 0, cur_end = 0;
+  SdfEval ev;
+  ev.w = ev.c = mk3(0, 0, 0);
+  ev.dr = ev.m = 0.0f;
+  ev.it = 0;
   while (true) {
     __syncwarp();
     unsigned idle = __ballot_sync(0xffffffffu, !have);
@@ -725,38 +735,50 @@ __global__ void __launch_bounds__(EXT_T, 8) k_extend_march(const __grid_constant
         first = true;
         have = true;
         ++rays;
+        if (FLAT) eval_start(ev, s_h, o);
       }
       cur_pos += min(avail, __popc(idle));
       idle = __ballot_sync(0xffffffffu, !have);
     }
     if (!__any_sync(0xffffffffu, have)) break;
     if (have) {
-      const f3 p = first ? o : fma3s(d, t, o);
-      const float dd = sdf_dist(s_h, p);
-      ++evals;
-      bool end = false;
-      if (first) {
-        t = dd;
-        steps = 0;
-        first = false;
-        end = t != t;
+      float dd = 0.0f;
+      bool ready = true;
+      if (FLAT) {
+        if (eval_more(ev, s_h)) eval_step(ev, s_h);
+        ready = !eval_more(ev, s_h);
+        if (ready) dd = eval_finish(ev, s_h);
       } else {
-        const bool hit = dm::abs(dd) < dm::max(c0, c1 * thr.at(t));
-        const bool gt = t > closest;
-        if (hit || gt) {
-          end = true;
-        } else {
-          t = t + dd;
-          ++steps;
-          end = (t != t) || steps >= max_marches;
-        }
+        dd = sdf_dist(s_h, first ? o : fma3s(d, t, o));
       }
-      if (end) {
-        if (t < closest) {  // hitable.rs:190-193
-          pb.d_t[g].w = t;
-          pb.q_key[q] = hk;
+      if (ready) {
+        ++evals;
+        bool end = false;
+        if (first) {
+          t = dd;
+          steps = 0;
+          first = false;
+          end = t != t;
+        } else {
+          const bool hit = dm::abs(dd) < dm::max(c0, c1 * thr.at(t));
+          const bool gt = t > closest;
+          if (hit || gt) {
+            end = true;
+          } else {
+            t = t + dd;
+            ++steps;
+            end = (t != t) || steps >= max_marches;
+          }
         }
-        have = false;
+        if (end) {
+          if (t < closest) {  // hitable.rs:190-193
+            pb.d_t[g].w = t;
+            pb.q_key[q] = hk;
+          }
+          have = false;
+        } else if (FLAT) {
+          eval_start(ev, s_h, fma3s(d, t, o));
+        }
       }
     }
   }
@@ -1210,6 +1232,7 @@ __global__ void __launch_bounds__(128, 4) k_shade_pre(const __grid_constant__ De
 // K5: persistent shadow sphere-march over the pass-wide segment queue.
 // TracedSDF::occluded per lane (sdf.rs:25-57); occlusion clears the owner's bit.
 #define SHD_T 128
+template <bool FLAT>
 __global__ void __launch_bounds__(SHD_T, 8) k_shadow(const __grid_constant__ DevScene sc, const PassBufs pb, int* __restrict__ work_ctr) {
   __shared__ RaynHitable s_hit[RAYN_MAX_HITABLES];
   for (int k = threadIdx.x; k < sc.n_hit; k += SHD_T) s_hit[k] = sc.hit[k];
@@ -1225,6 +1248,10 @@ __global__ void __launch_bounds__(SHD_T, 8) k_shadow(const __grid_constant__ Dev
   float max_dist = 0.0f, t = 0.0f;
   int owner = 0, bit = 0, hk = 0, steps = 0, evals = 0;
   int cur_pos = 0, cur_end = 0;
+  SdfEval ev;
+  ev.w = ev.c = mk3(0, 0, 0);
+  ev.dr = ev.m = 0.0f;
+  ev.it = 0;
   while (true) {
     __syncwarp();
     unsigned idle = __ballot_sync(0xffffffffu, !have);
@@ -1254,30 +1281,43 @@ __global__ void __launch_bounds__(SHD_T, 8) k_shadow(const __grid_constant__ Dev
         owner = pb.seg_owner[idx];
         first = true;
         have = true;
+        if (FLAT) eval_start(ev, s_hit[hk], st);
       }
       cur_pos += min(avail, __popc(idle));
       idle = __ballot_sync(0xffffffffu, !have);
     }
     if (!__any_sync(0xffffffffu, have)) break;
     if (have) {
-      const f3 p = first ? st : fma3s(dir, t, st);
-      const float dd = sdf_dist(s_hit[hk], p);
-      ++evals;
-      bool done = false;
-      if (first) {
-        t = dd;
-        first = false;
-        steps = 0;
-        done = (t != t) || (t > max_dist);
-      } else if (dm::abs(dd) < dm::max(oc0, oc1 * t)) {
-        atomicAnd(pb.vis + owner, ~(1u << bit));  // occluded
-        done = true;
+      float dd = 0.0f;
+      bool ready = true;
+      if (FLAT) {
+        if (eval_more(ev, s_hit[hk])) eval_step(ev, s_hit[hk]);
+        ready = !eval_more(ev, s_hit[hk]);
+        if (ready) dd = eval_finish(ev, s_hit[hk]);
       } else {
-        t = t + dd;
-        ++steps;
-        done = (t != t) || steps >= max_vis || (t > max_dist);
+        dd = sdf_dist(s_hit[hk], first ? st : fma3s(dir, t, st));
       }
-      if (done) have = false;
+      if (ready) {
+        ++evals;
+        bool done = false;
+        if (first) {
+          t = dd;
+          first = false;
+          steps = 0;
+          done = (t != t) || (t > max_dist);
+        } else if (dm::abs(dd) < dm::max(oc0, oc1 * t)) {
+          atomicAnd(pb.vis + owner, ~(1u << bit));  // occluded
+          done = true;
+        } else {
+          t = t + dd;
+          ++steps;
+          done = (t != t) || steps >= max_vis || (t > max_dist);
+        }
+        if (done)
+          have = false;
+        else if (FLAT)
+          eval_start(ev, s_hit[hk], fma3s(dir, t, st));
+      }
     }
   }
   warp_add(pb.counters + CNT_EVALS_SHADOW, evals);

@@ -274,7 +274,7 @@ def test_alternative_kernel_families_stay_bit_exact(oracle):
     for n, res, samples, mb in [(3, (48, 48), 2, 4), (4, (32, 32), 1, 2)]:
         c, inp = small_config(n, res, samples, mb)
         o, _ = oracle.render(c["world"], c["camera"], inp, (16, 16), c["integrator"], TR)
-        for flag in (L.FLAG_SIMPLE_MARCH, L.FLAG_BLOCK_POOL):
+        for flag in (L.FLAG_SIMPLE_MARCH, L.FLAG_BLOCK_POOL, L.FLAG_FLATTEN):
             r = Renderer(0, flags=flag)
             try:
                 r.upload_scene(c["world"], c["camera"])
