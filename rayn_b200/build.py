@@ -31,6 +31,8 @@ def needs_build():
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
+        if not os.path.exists(os.path.join(OUT_DIR, "rayn_host")):
+            build_host()
         return OUT
     os.makedirs(OUT_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -40,7 +42,17 @@ def build(force=False, verbose=False):
         sys.stderr.write(r.stdout + r.stderr)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed building librayn_b200.so")
+    build_host()
     return OUT
+
+
+def build_host():
+    """C++ host stand-in (rayn_b200/host): links against the C ABI only."""
+    r = subprocess.run(["make", "-C", os.path.join(HERE, "host"), "-B"], capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("building rayn_host failed")
+    return os.path.join(OUT_DIR, "rayn_host")
 
 
 if __name__ == "__main__":

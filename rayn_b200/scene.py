@@ -227,7 +227,8 @@ class SphereLight:  # light.rs:27-34
 # ---- cameras (camera.rs) ----------------------------------------------------------------------------
 def _fov_half(resolution, vfov):
     theta = f32(vfov) * f32(math.pi) / f32(180.0)
-    half_height = np.tan(theta / f32(2.0), dtype=np.float32)
+    # f32::tan -> libm tanf; numpy's float32 tan is 1 ulp off for 30 degrees, so round the double result instead
+    half_height = f32(math.tan(float(theta / f32(2.0))))
     aspect = f32(resolution[0]) / f32(resolution[1])
     half_width = aspect * half_height
     return f32(half_width), f32(half_height)

@@ -133,3 +133,21 @@ def test_gather_with_a_fake_collective():
         got = gather_film_arrays(parts[r], w, h, tile, r, world, lambda v: slabs)
         for k in full:
             assert np.array_equal(got[k], full[k])
+
+
+def test_cpp_host_flattens_the_same_scene_as_the_python_host(tmp_path):
+    """rayn_b200/host (C++ stand-in for setup.rs/main.rs) and rayn_b200/scene.py must hand the C ABI
+    byte-identical descriptors for every BASELINE config (no GPU needed: --dump-scene stops before rendering)."""
+    import os
+    import subprocess
+    from rayn_b200 import build
+    build.build()
+    exe = os.path.join(os.path.dirname(build.OUT), "rayn_host")
+    for n in (1, 2, 3, 4, 5):
+        out = tmp_path / f"scene{n}.bin"
+        subprocess.run([exe, "--config", str(n), "--res", "160", "90", "--dump-scene", str(out)], check=True)
+        c = configs.baseline_config(n, res=(160, 90))
+        d, keep = c["world"].flatten(c["camera"])
+        want = b"".join(bytes(d.hitables[i]) for i in range(d.n_hitables)) + b"".join(bytes(d.materials[i]) for i in range(d.n_materials)) + \
+            b"".join(bytes(d.lights[i]) for i in range(d.n_lights)) + bytes(d.camera) + bytes(d.volume)
+        assert out.read_bytes() == want, f"config {n}"

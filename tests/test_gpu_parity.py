@@ -283,3 +283,23 @@ def test_alternative_kernel_families_stay_bit_exact(oracle):
                 r.close()
             for ch in CH:
                 assert_bit_equal(g[ch], o[ch], f"kernel family {flag} cfg{n} {ch}")
+
+
+def test_cpp_host_renders_the_same_film_as_the_python_host(renderer, tmp_path):
+    """End to end through the C++ stand-in for main.rs (rayn_b200/host/main.cpp)."""
+    import os
+    import subprocess
+    from rayn_b200 import build
+    exe = os.path.join(os.path.dirname(build.OUT), "rayn_host")
+    out = tmp_path / "planes.bin"
+    r = subprocess.run([exe, "--config", "3", "--res", "48", "32", "--samples", "2", "--bounces", "3", "--dump", str(out)],
+                       capture_output=True, text=True, check=True)
+    assert "Done in" in r.stdout
+    c, inp = small_config(3, (48, 32), 2, 3)
+    renderer.upload_scene(c["world"], c["camera"])
+    g = renderer.render_host(inp, (16, 16), c["integrator"], TR)
+    raw = np.fromfile(out, np.float32)
+    npx = 48 * 32
+    got = {"color": raw[:3 * npx], "alpha": raw[3 * npx:4 * npx], "background": raw[4 * npx:7 * npx], "normal": raw[7 * npx:]}
+    for ch in CH:
+        assert_bit_equal(got[ch], g[ch], f"C++ host {ch}")
