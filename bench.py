@@ -134,6 +134,8 @@ def cpu_sample(c, inputs, target_seconds, threads=0):
     w, h = c["res"]
     n_tiles = int(np.prod(tile_grid(w, h, 16, 16)))
     ncores = os.cpu_count() or 1
+    if threads == 0:
+        threads = ncores  # explicit: torchrun exports OMP_NUM_THREADS=1, which would silently serialise the CPU baseline
     # probe: a spread of ~2*ncores tiles, to size the real sample
     k = max(1, n_tiles // max(2 * ncores, 8))
     t = time.perf_counter()
@@ -148,7 +150,7 @@ def cpu_sample(c, inputs, target_seconds, threads=0):
         dt = time.perf_counter() - t
         k = k2
     samples_done = info["tiles"] * 256 * c["spp"]
-    return dict(value=samples_done / dt / 1e6, unit="Msamples/s", cores=ncores if threads == 0 else threads, kind="port",
+    return dict(value=samples_done / dt / 1e6, unit="Msamples/s", cores=threads, kind="port",
                 sample=f"every {k}-th 16x16 tile of the workload ({info['tiles']} of {n_tiles} tiles, {samples_done / 1e6:.2f} Msamples, {dt:.1f} s), "
                        f"OpenMP over tiles like rayon; C++ SSE-packet restatement of rayn's path (rayn itself cannot be built here)"), dt
 
