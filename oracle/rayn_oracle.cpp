@@ -407,17 +407,18 @@ inline F4 mandelbulb_dist(const RaynHitable& h, V3 p) {
     // polar part: a = z^2, b = r^2
     F4 a = w.z * w.z, b = m;
     F4 b2 = b * b, b3 = b2 * b, b4 = b2 * b2;
-    F4 P = (((splat(128.0f) * a - splat(256.0f) * b) * a + splat(160.0f) * b2) * a - splat(32.0f) * b3) * a + b4;
-    F4 A = ((splat(128.0f) * a - splat(192.0f) * b) * a + splat(80.0f) * b2) * a - splat(8.0f) * b3;
+    // Horner forms with explicit fused multiply-adds (the definition is ours: DESIGN.md §7)
+    F4 P = mul_add(mul_add(mul_add(mul_add(splat(128.0f), a, splat(-256.0f) * b), a, splat(160.0f) * b2), a, splat(-32.0f) * b3), a, b4);
+    F4 A = mul_add(mul_add(mul_add(splat(128.0f), a, splat(-192.0f) * b), a, splat(80.0f) * b2), a, splat(-8.0f) * b3);
     // azimuth part: a' = x^2, b' = rho^2
     F4 ax = w.x * w.x;
     F4 q = mul_add(w.x, w.x, w.y * w.y);
     F4 q2 = q * q, q3 = q2 * q, q4 = q2 * q2;
-    F4 C = (((splat(128.0f) * ax - splat(256.0f) * q) * ax + splat(160.0f) * q2) * ax - splat(32.0f) * q3) * ax + q4;
-    F4 B = ((splat(128.0f) * ax - splat(192.0f) * q) * ax + splat(80.0f) * q2) * ax - splat(8.0f) * q3;
+    F4 C = mul_add(mul_add(mul_add(mul_add(splat(128.0f), ax, splat(-256.0f) * q), ax, splat(160.0f) * q2), ax, splat(-32.0f) * q3), ax, q4);
+    F4 B = mul_add(mul_add(mul_add(splat(128.0f), ax, splat(-192.0f) * q), ax, splat(80.0f) * q2), ax, splat(-8.0f) * q3);
     F4 k = (w.z * A) / (q3 * f4sqrt(q));
     k = merge(cmp_gt(q, splat(0.0f)), k, splat(0.0f));
-    V3 nw = {k * C + p.x, k * (w.x * w.y * B) + p.y, P + p.z};
+    V3 nw = {mul_add(k, C, p.x), mul_add(k, w.x * w.y * B, p.y), P + p.z};
     F4 nm = dot(nw, nw);
     w = v3merge(esc, w, nw);
     dr = merge(esc, dr, ndr);

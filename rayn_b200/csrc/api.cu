@@ -376,6 +376,7 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
   CU(cudaMemsetAsync(pb.counters, 0, 8 * sizeof(unsigned long long), st));
   int np = 2;
   while (np < spp) np <<= 1;
+  CU(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resolve_smem_bytes(np)));
   if (block_pool) CU(cudaFuncSetAttribute(k_shade2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_smem_bytes(n_sdf)));
 
   std::vector<int> h_nslots, h_slots;
@@ -470,7 +471,7 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
       }
     }
     timed_begin(ctx, RAYN_K_RESOLVE);
-    k_resolve<<<dim3(f->tile_w * f->tile_h, nt), RES_T, (size_t)np * 8, st>>>(fr, pb, p_color, p_alpha, p_bg, p_normal, np);
+    k_resolve<<<dim3(f->tile_w * f->tile_h, nt), RES_T, resolve_smem_bytes(np), st>>>(fr, pb, p_color, p_alpha, p_bg, p_normal, np);
     timed_end(ctx, RAYN_K_RESOLVE);
     CU(cudaGetLastError());
   }

@@ -167,16 +167,17 @@ RT_D void eval_step(SdfEval& e, const RaynHitable& h) {
     e.dr = dm::fma(8.0f * r7, e.dr, 1.0f);
     const float a = w.z * w.z, b = m;
     const float b2 = b * b, b3 = b2 * b, b4 = b2 * b2;
-    const float P = (((128.0f * a - 256.0f * b) * a + 160.0f * b2) * a - 32.0f * b3) * a + b4;
-    const float A = ((128.0f * a - 192.0f * b) * a + 80.0f * b2) * a - 8.0f * b3;
+    // Horner forms with explicit fused multiply-adds (the definition is ours: DESIGN.md §7)
+    const float P = dm::fma(dm::fma(dm::fma(dm::fma(128.0f, a, -256.0f * b), a, 160.0f * b2), a, -32.0f * b3), a, b4);
+    const float A = dm::fma(dm::fma(dm::fma(128.0f, a, -192.0f * b), a, 80.0f * b2), a, -8.0f * b3);
     const float ax = w.x * w.x;
     const float q = dm::fma(w.x, w.x, w.y * w.y);
     const float q2 = q * q, q3 = q2 * q, q4 = q2 * q2;
-    const float C = (((128.0f * ax - 256.0f * q) * ax + 160.0f * q2) * ax - 32.0f * q3) * ax + q4;
-    const float B = ((128.0f * ax - 192.0f * q) * ax + 80.0f * q2) * ax - 8.0f * q3;
+    const float C = dm::fma(dm::fma(dm::fma(dm::fma(128.0f, ax, -256.0f * q), ax, 160.0f * q2), ax, -32.0f * q3), ax, q4);
+    const float B = dm::fma(dm::fma(dm::fma(128.0f, ax, -192.0f * q), ax, 80.0f * q2), ax, -8.0f * q3);
     float k = (w.z * A) / (q3 * sqrtf(q));
     k = q > 0.0f ? k : 0.0f;
-    e.w = mk3(k * C + e.c.x, k * (w.x * w.y * B) + e.c.y, P + e.c.z);
+    e.w = mk3(dm::fma(k, C, e.c.x), dm::fma(k, w.x * w.y * B, e.c.y), P + e.c.z);
     e.m = dot(e.w, e.w);
   } else {
     const float l = h.box_l, nl = -h.box_l;
@@ -323,7 +324,7 @@ struct ShadingPoint {  // hitable.rs:21-28 (per lane)
   m3 basis;
 };
 // sdf.rs:85-101 with sdfu's tetrahedral normals_fast (oracle/README.md A8); sphere.rs:74-86
-RT_D void shading_info(const DevScene& sc, const RaynHitable& h, Thr thr, ShadingPoint& sp, int* evals) {
+RT_D void shading_info(const DevScene& sc, const RaynHitable& h, Thr thr, ShadingPoint& sp, int* evals, bool want_basis = true) {
   sp.point = fma3s(sp.d, sp.t, sp.o);  // WHit::point -> ray.point_at, ray.rs:22-24
   if (h.kind == RAYN_HITABLE_SPHERE) {
     sp.normal = normalized(sp.point - ld3(h.center));
@@ -340,7 +341,7 @@ RT_D void shading_info(const DevScene& sc, const RaynHitable& h, Thr thr, Shadin
     sp.normal = normalized(n);
     sp.offset_by = eps;
   }
-  sp.basis = onb(sp.normal);
+  if (want_basis) sp.basis = onb(sp.normal);
 }
 
 // ---- lights, light.rs ---------------------------------------------------------------------------

@@ -1173,18 +1173,27 @@ __global__ void __launch_bounds__(128, 4) k_shade_pre(const __grid_constant__ De
     sp.d = mk3(d4.x, d4.y, d4.z);
     sp.time = o4.w;
     sp.t = d4.w;
-    shading_info(sc, h, thr, sp, &evals);
-    pb.nrm[g] = make_float4(sp.normal.x, sp.normal.y, sp.normal.z, sp.offset_by);
-    const f3 wo = -sp.d;
-    const bool has_ext = sc.vol.has_extinction != 0;
-    const float neg_rho_t = -sc.vol.coeff_extinction;
-    const float vt = has_ext ? dm::exp(neg_rho_t * sp.t) : 1.0f;                          // integrator.rs:64-68
-    const f3 radiance = mk3(r4.x, r4.y, r4.z) + bsdf_le(mat, wo) * mk3(t4.x, t4.y, t4.z) * vt;  // :70-71
-    pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
     const bool recv = receives_light(mat);
     const int nl = sc.n_lights;
     const bool scat = sc.vol.has_scattering != 0 && nl > 0;
     const int n_rounds = nl > 0 ? 1 + (scat ? fr.vm : 0) : 0;
+    const f3 wo = -sp.d;
+    const bool has_ext = sc.vol.has_extinction != 0;
+    const float neg_rho_t = -sc.vol.coeff_extinction;
+    const float vt = has_ext ? dm::exp(neg_rho_t * sp.t) : 1.0f;  // integrator.rs:64-68
+    if (!recv && !scat) {
+      // Sky / Emissive without volumetrics: emission is the whole shading step (integrator.rs:70-71,
+      // 189-203); the path ends here.  Every lane of its packet has the same material, so nobody needs
+      // this lane's light choice and k_shade_post can treat the slot as empty.
+      const f3 radiance = mk3(r4.x, r4.y, r4.z) + bsdf_le(mat, wo) * mk3(t4.x, t4.y, t4.z) * vt;
+      pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+      pb.term[g] = ((depth == 0 ? TERM_BACKGROUND : TERM_COLOR) << 30) | ((unsigned)depth << 20) | (unsigned)s;
+      pb.q_shade[(size_t)ts * pb.QS + s] = -1;
+    } else {
+    shading_info(sc, h, thr, sp, &evals, false);
+    pb.nrm[g] = make_float4(sp.normal.x, sp.normal.y, sp.normal.z, sp.offset_by);
+    const f3 radiance = mk3(r4.x, r4.y, r4.z) + bsdf_le(mat, wo) * mk3(t4.x, t4.y, t4.z) * vt;  // :70-71
+    pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
     unsigned vis = 0xffffffffu;
     for (int round = (recv ? 0 : 1); round < n_rounds; ++round) {
       const unsigned wr = round == 0 ? cx.w0 : (round == 1 ? cx.w1 : cx.w2);
@@ -1224,6 +1233,7 @@ __global__ void __launch_bounds__(128, 4) k_shade_pre(const __grid_constant__ De
       }
     }
     pb.vis[g] = vis;
+    }
   }
   warp_add(pb.counters + CNT_EVALS_SHADOW, evals);
   warp_add(pb.counters + CNT_SHADOW_RAYS, shadows);
@@ -1472,14 +1482,26 @@ RT_D void bitonic_sort(uint32_t* key, int* val, int np) {
     }
   }
 }
+// sorts (key,val) ascending unless the keys already are (the common case: every path of the
+// pixel hit the same object at depth 0, so slot order == sample order)
+RT_D void sort_if_needed(uint32_t* key, int* val, int np) {
+  int bad = 0;
+  for (int i = threadIdx.x; i + 1 < np; i += RES_T) bad |= key[i] > key[i + 1];
+  if (__syncthreads_or(bad)) bitonic_sort(key, val, np);
+}
+
+static inline size_t resolve_smem_bytes(int np) { return (size_t)np * (2 * 4 + 7 * 4 + 4); }
 
 __global__ void __launch_bounds__(RES_T) k_resolve(const DevFrame fr, const PassBufs pb, float* __restrict__ color,
                                                    float* __restrict__ alpha, float* __restrict__ background,
                                                    float* __restrict__ normal, const int np) {
-  extern __shared__ unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* key = reinterpret_cast<uint32_t*>(smem_raw);
-  int* val = reinterpret_cast<int*>(smem_raw) + np;
-  __shared__ int n_sorted;
+  int* val = reinterpret_cast<int*>(key + np);
+  float* rx = reinterpret_cast<float*>(val + np);
+  float *ry = rx + np, *rz = ry + np, *nx = rz + np, *ny = nx + np, *nz = ny + np;
+  uint32_t* s0 = reinterpret_cast<uint32_t*>(nz + np);   // depth-0 slot + 1 (0 = no Alpha/WorldNormal sample)
+  uint32_t* tw = s0 + np;                                // termination word
   const int ts = blockIdx.y, pl = blockIdx.x, tid = threadIdx.x;
   const TileGeom tg = tile_geom(fr, pb.tile_ids[ts]);
   if (pl >= tg.tw * tg.th) return;
@@ -1487,24 +1509,32 @@ __global__ void __launch_bounds__(RES_T) k_resolve(const DevFrame fr, const Pass
   const size_t pix = (size_t)(tg.x0 + xl) + (size_t)(tg.y0 + yl) * fr.W;
   const size_t g0 = (size_t)ts * pb.R + (size_t)pl * fr.spp;
   const float div = (float)fr.spp;
-
-  // ---- sort A: depth-0 receives_light hits by slot0 -> WorldNormal, Alpha
+  // stage the pixel's spp paths in shared memory with coalesced loads
   for (int i = tid; i < np; i += RES_T) {
-    uint32_t k = 0xffffffffu;
+    uint32_t k = 0xffffffffu, slot0 = 0, term = 0;
+    float4 r4 = make_float4(0, 0, 0, 0), n4 = r4;
     if (i < fr.spp) {
-      const uint32_t s0 = __float_as_uint(pb.nrm0[g0 + i].w);
-      if (s0) k = s0;
+      r4 = pb.rad[g0 + i];
+      n4 = pb.nrm0[g0 + i];
+      term = pb.term[g0 + i];
+      slot0 = __float_as_uint(n4.w);
+      if (slot0) k = slot0;
     }
+    rx[i] = r4.x, ry[i] = r4.y, rz[i] = r4.z;
+    nx[i] = n4.x, ny[i] = n4.y, nz[i] = n4.z;
+    s0[i] = slot0;
+    tw[i] = term;
     key[i] = k;
     val[i] = i;
   }
   __syncthreads();
-  bitonic_sort(key, val, np);
+  // ---- order A: depth-0 receives_light hits by slot -> WorldNormal, Alpha (integrator.rs:161-169)
+  sort_if_needed(key, val, np);
   if (tid < 4) {
     float acc = 0.0f;
     for (int i = 0; i < np && key[i] != 0xffffffffu; ++i) {
-      const float4 n4 = pb.nrm0[g0 + val[i]];
-      acc += tid == 0 ? n4.x : tid == 1 ? n4.y : tid == 2 ? n4.z : 1.0f;
+      const int v = val[i];
+      acc += tid == 0 ? nx[v] : tid == 1 ? ny[v] : tid == 2 ? nz[v] : 1.0f;
     }
     if (tid < 3)
       normal[3 * pix + tid] = acc / div;
@@ -1512,35 +1542,28 @@ __global__ void __launch_bounds__(RES_T) k_resolve(const DevFrame fr, const Pass
       alpha[pix] = acc / div;
   }
   __syncthreads();
-  // ---- sort B: terminated paths by (depth, slot) -> Color / Background
+  // ---- order B: terminated paths by (depth, slot) -> Color / Background (integrator.rs:178-203)
   for (int i = tid; i < np; i += RES_T) {
-    uint32_t k = 0xffffffffu;
-    if (i < fr.spp) {
-      const uint32_t t = pb.term[g0 + i];
-      if (t >> 30) k = t & 0x3fffffffu;
-    }
-    key[i] = k;
+    const uint32_t t = tw[i];
+    key[i] = (i < fr.spp && (t >> 30)) ? (t & 0x3fffffffu) : 0xffffffffu;
     val[i] = i;
   }
   __syncthreads();
-  bitonic_sort(key, val, np);
+  sort_if_needed(key, val, np);
   if (tid < 6) {
     const int ch = tid % 3;
     const uint32_t want = tid < 3 ? TERM_COLOR : TERM_BACKGROUND;
+    const float* src = ch == 0 ? rx : ch == 1 ? ry : rz;
     float acc = 0.0f;
     for (int i = 0; i < np && key[i] != 0xffffffffu; ++i) {
-      const size_t g = g0 + val[i];
-      if ((pb.term[g] >> 30) == want) {
-        const float4 r4 = pb.rad[g];
-        acc += ch == 0 ? r4.x : ch == 1 ? r4.y : r4.z;
-      }
+      const int v = val[i];
+      if ((tw[v] >> 30) == want) acc += src[v];
     }
     if (tid < 3)
       color[3 * pix + ch] = acc / div;
     else
       background[3 * pix + ch] = acc / div;
   }
-  (void)n_sorted;
 }
 
 // ------------------------------------------------------------------------------------------
