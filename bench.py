@@ -123,7 +123,7 @@ def workload_name(c, args, world):
     w, h = c["res"]
     s = f"{c['name'].split('-')[0]} {'Mandelbulb(authored)' if 'mandelbulb' in c['name'] else c['name'].split('-')[1]} {w}x{h} {c['spp']}spp {c['max_bounces']}b"
     if world > 1:
-        s += f" tiles%{world} ({args.scaling}: spp {'x' + str(world) if args.scaling == 'weak' else 'fixed'})"
+        s += f" tiles (tx+ty)%{world} ({args.scaling}: spp {'x' + str(world) if args.scaling == 'weak' else 'fixed'})"
     return s
 
 
@@ -218,7 +218,7 @@ def main():
     r = Renderer(local_rank, max_paths_per_pass=args.max_paths, flags=args.flags)
     r.upload_scene(c["world"], c["camera"])
     film = DistFilm(r, w, h, tile, rank, world)
-    fdesc = device_frame_desc(inputs_dev, w, h, tile, c["samples"], c["integrator"], 1, c["time_range"], rank, world, sets)
+    fdesc = device_frame_desc(inputs_dev, w, h, tile, c["samples"], c["integrator"], 1, c["time_range"], sets, film.tile_list)
 
     def step_resident():
         film.render(fdesc)
@@ -328,7 +328,7 @@ def main():
         out_pin = torch.zeros(10 * npx, dtype=torch.float32).pin_memory()
         hp = L.RaynFilmPlanes(out_pin.data_ptr(), out_pin[3 * npx:].data_ptr(), out_pin[4 * npx:].data_ptr(), out_pin[7 * npx:].data_ptr(), L.MEM_HOST)
         hdesc = make_frame_desc(w, h, tile, c["samples"], c["integrator"], 1, c["time_range"], tuple(t.data_ptr() for t in pin), L.MEM_HOST,
-                                rank, world, sets)
+                                0, 1, sets, film.tile_list)
         h2d = sum(t.numel() * 4 for t in pin)
         d2h = out_pin.numel() * 4
 
@@ -367,7 +367,7 @@ def main():
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_name(c, args, world), "tile": "16x16", "samples_total": int(total_samples),
                            "l2": "working set (path state >= 3 GB/pass) far exceeds the 126 MB L2; no explicit flush",
-                           "parallelism": f"tiles%{world}" if world > 1 else "1 GPU"},
+                           "parallelism": f"dp{world}: 16x16 film tiles, (tx+ty)%{world} interleave, NCCL all-gather of the film" if world > 1 else "1 GPU"},
                 "clocks": clock_info, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "kernels": per_kernel, "wall_ms_per_step": wall_ms / args.steps, "passes_per_step": int(st.passes)}
         print(json.dumps(line), flush=True)

@@ -173,6 +173,11 @@ typedef struct RaynFrameDesc {
    * tile_index = tile_x * n_tiles_y + tile_y (film.rs:401-425).  1-GPU: stride 1, offset 0. */
   int32_t tile_offset;
   int32_t tile_stride;
+  /* optional explicit shard: if tile_list != NULL (HOST pointer, n_tile_list entries, each a
+   * tile_index, ascending) it replaces offset/stride.  Lets the host pick any interleave,
+   * e.g. the diagonal (tile_x + tile_y) % N that balances centre-weighted fractal scenes.      */
+  const int32_t* tile_list;
+  int32_t n_tile_list;
 } RaynFrameDesc;
 
 /* ---- Film channel planes (src/film.rs:103-120), row-major, y up, already / spp ------ */
@@ -247,16 +252,16 @@ int32_t rayn_b200_get_stats(const RaynContext* ctx, RaynStats* out);
 
 /* ---- multi-GPU film gather helpers (device pointers) --------------------------------
  * Tiles are disjoint (film.rs:82-98), so the gather MOVES bytes, it never reduces.
- * pack: copies this rank's tiles out of full-size planes into a dense slab
- *       [n_my_tiles][10][tile_w*tile_h] (channel order: color rgb, alpha, bg rgb, normal xyz)
+ * pack: copies the listed tiles out of full-size planes into a dense slab
+ *       [n_tiles][10][tile_w*tile_h] (channel order: color rgb, alpha, bg rgb, normal xyz)
  * unpack: scatters one rank's slab back into full-size planes.                           */
-int64_t rayn_b200_film_slab_floats(int32_t width, int32_t height, int32_t tile_w, int32_t tile_h,
-                                   int32_t tile_offset, int32_t tile_stride);
+int64_t rayn_b200_film_slab_floats(int32_t tile_w, int32_t tile_h, int32_t n_tiles);
+/* tile_list: HOST pointer to n_tiles tile indices (the shard whose slab this is) */
 int32_t rayn_b200_film_pack_tiles(RaynContext* ctx, int32_t width, int32_t height, int32_t tile_w,
-                                  int32_t tile_h, int32_t tile_offset, int32_t tile_stride,
+                                  int32_t tile_h, const int32_t* tile_list, int32_t n_tiles,
                                   const RaynFilmPlanes* planes_dev, float* slab_dev);
 int32_t rayn_b200_film_unpack_tiles(RaynContext* ctx, int32_t width, int32_t height, int32_t tile_w,
-                                    int32_t tile_h, int32_t tile_offset, int32_t tile_stride,
+                                    int32_t tile_h, const int32_t* tile_list, int32_t n_tiles,
                                     const float* slab_dev, const RaynFilmPlanes* planes_dev);
 
 /* ---- host-side input builders (pure CPU; stand in for crates the Rust host owns) ----

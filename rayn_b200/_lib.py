@@ -78,7 +78,7 @@ class RaynFrameDesc(C.Structure):
                 ("max_bounces", i32), ("volume_marches", i32), ("frame", i32), ("t0", f32), ("t1", f32),
                 ("sets_1d", i32), ("sets_2d", i32), ("samples_1d", C.c_void_p), ("samples_2d", C.c_void_p),
                 ("scramble", C.c_void_p), ("fis_inverse_cdf", C.c_void_p), ("input_space", i32),
-                ("tile_offset", i32), ("tile_stride", i32)]
+                ("tile_offset", i32), ("tile_stride", i32), ("tile_list", C.POINTER(i32)), ("n_tile_list", i32)]
 
 
 class RaynFilmPlanes(C.Structure):
@@ -106,9 +106,9 @@ SYMBOLS = {
     "rayn_b200_upload_scene": (i32, [C.c_void_p, C.POINTER(RaynSceneDesc)]),
     "rayn_b200_render_frame": (i32, [C.c_void_p, C.POINTER(RaynFrameDesc), C.POINTER(RaynFilmPlanes)]),
     "rayn_b200_get_stats": (i32, [C.c_void_p, C.POINTER(RaynStats)]),
-    "rayn_b200_film_slab_floats": (i64, [i32, i32, i32, i32, i32, i32]),
-    "rayn_b200_film_pack_tiles": (i32, [C.c_void_p, i32, i32, i32, i32, i32, i32, C.POINTER(RaynFilmPlanes), C.c_void_p]),
-    "rayn_b200_film_unpack_tiles": (i32, [C.c_void_p, i32, i32, i32, i32, i32, i32, C.c_void_p, C.POINTER(RaynFilmPlanes)]),
+    "rayn_b200_film_slab_floats": (i64, [i32, i32, i32]),
+    "rayn_b200_film_pack_tiles": (i32, [C.c_void_p, i32, i32, i32, i32, C.POINTER(i32), i32, C.POINTER(RaynFilmPlanes), C.c_void_p]),
+    "rayn_b200_film_unpack_tiles": (i32, [C.c_void_p, i32, i32, i32, i32, C.POINTER(i32), i32, C.c_void_p, C.POINTER(RaynFilmPlanes)]),
     "rayn_b200_host_rd_tables": (i32, [i32, i32, i32, C.c_uint64, fp, fp]),
     "rayn_b200_host_scramble": (i32, [i32, i32, fp]),
     "rayn_b200_host_fis_blackman_harris": (i32, [f32, fp]),

@@ -42,6 +42,8 @@ struct RaynContext {
   size_t cap_s1 = 0, cap_s2 = 0, cap_scr = 0;
   float* d_planes = nullptr;
   size_t cap_planes = 0;
+  int* d_pack_ids = nullptr;
+  size_t cap_pack_ids = 0;
   RaynStats stats;
   bool qlog_enabled = false;
   std::vector<int32_t> qlog;
@@ -215,6 +217,7 @@ void rayn_b200_destroy(RaynContext* ctx) {
   free_pass(ctx);
   cudaFree(ctx->pb.counters);
   cudaFree(ctx->d_work_ctr);
+  cudaFree(ctx->d_pack_ids);
   cudaFree(ctx->d_s1), cudaFree(ctx->d_s2), cudaFree(ctx->d_scr), cudaFree(ctx->d_fis), cudaFree(ctx->d_planes);
   for (auto& t : ctx->timed) cudaEventDestroy(t.a), cudaEventDestroy(t.b);
   cudaEventDestroy(ctx->ev0), cudaEventDestroy(ctx->ev1);
@@ -320,7 +323,17 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
   fr.t0 = f->t0, fr.t1 = f->t1;
 
   std::vector<int> my_tiles;
-  for (int idx = f->tile_offset; idx < fr.ntx * fr.nty; idx += stride) my_tiles.push_back(idx);
+  if (f->tile_list) {
+    if (f->n_tile_list < 0) return fail(ctx, RAYN_ERR_INVALID_ARG, "n_tile_list < 0");
+    for (int i = 0; i < f->n_tile_list; ++i) {
+      const int idx = f->tile_list[i];
+      if (idx < 0 || idx >= fr.ntx * fr.nty || (i && idx <= f->tile_list[i - 1]))
+        return fail(ctx, RAYN_ERR_INVALID_ARG, "tile_list must be ascending tile indices in [0,%d)", fr.ntx * fr.nty);
+      my_tiles.push_back(idx);
+    }
+  } else {
+    for (int idx = f->tile_offset; idx < fr.ntx * fr.nty; idx += stride) my_tiles.push_back(idx);
+  }
 
   memset(&ctx->stats, 0, sizeof ctx->stats);
   ctx->timed_used = 0;
@@ -511,38 +524,35 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
 }
 
 // ---- multi-GPU film gather helpers ------------------------------------------------------------------
-static int tiles_of(int W, int H, int tw, int th, int off, int stride, int* nty_out, int* total_out) {
-  const int ntx = (W + W % tw) / tw, nty = (H + H % th) / th;
-  if (nty_out) *nty_out = nty;
-  if (total_out) *total_out = ntx * nty;
-  const int total = ntx * nty;
-  return off < total ? (total - off + stride - 1) / stride : 0;
+int64_t rayn_b200_film_slab_floats(int32_t tw, int32_t th, int32_t n_tiles) {
+  if (tw <= 0 || th <= 0 || n_tiles < 0) return -1;
+  return (int64_t)n_tiles * 10 * tw * th;
 }
-int64_t rayn_b200_film_slab_floats(int32_t W, int32_t H, int32_t tw, int32_t th, int32_t off, int32_t stride) {
-  if (W <= 0 || H <= 0 || tw <= 0 || th <= 0 || stride <= 0 || off < 0) return -1;
-  return (int64_t)tiles_of(W, H, tw, th, off, stride, nullptr, nullptr) * 10 * tw * th;
-}
-static int32_t pack_unpack(RaynContext* ctx, int W, int H, int tw, int th, int off, int stride, const RaynFilmPlanes* pl, float* slab,
-                           int unpack) {
-  if (!ctx || !pl || !slab || stride <= 0 || off < 0) return fail(ctx, RAYN_ERR_INVALID_ARG, "film pack/unpack: bad argument");
-  CU(cudaSetDevice(ctx->device));
-  int nty, total;
-  const int n = tiles_of(W, H, tw, th, off, stride, &nty, &total);
+static int32_t pack_unpack(RaynContext* ctx, int W, int H, int tw, int th, const int32_t* tile_list, int n, const RaynFilmPlanes* pl,
+                           float* slab, int unpack) {
+  if (!ctx || !pl || !slab || n < 0 || (n && !tile_list) || W <= 0 || H <= 0 || tw <= 0 || th <= 0)
+    return fail(ctx, RAYN_ERR_INVALID_ARG, "film pack/unpack: bad argument");
   if (n == 0) return RAYN_OK;
+  CU(cudaSetDevice(ctx->device));
+  const int ntx = (W + W % tw) / tw, nty = (H + H % th) / th;
+  for (int i = 0; i < n; ++i)
+    if (tile_list[i] < 0 || tile_list[i] >= ntx * nty) return fail(ctx, RAYN_ERR_INVALID_ARG, "film pack/unpack: tile %d out of range", tile_list[i]);
+  CU(regrow(&ctx->d_pack_ids, &ctx->cap_pack_ids, (size_t)n));
   CU(cudaDeviceSynchronize());
-  k_film_pack<<<n, 256, 0, ctx->stream>>>(W, H, tw, th, nty, total, off, stride, pl->color, pl->alpha, pl->background, pl->normal, slab,
-                                          unpack, pl->color, pl->alpha, pl->background, pl->normal);
+  CU(cudaMemcpyAsync(ctx->d_pack_ids, tile_list, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  k_film_pack<<<n, 256, 0, ctx->stream>>>(W, H, tw, th, nty, ctx->d_pack_ids, pl->color, pl->alpha, pl->background, pl->normal, slab, unpack,
+                                          pl->color, pl->alpha, pl->background, pl->normal);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(ctx->stream));
   return RAYN_OK;
 }
-int32_t rayn_b200_film_pack_tiles(RaynContext* ctx, int32_t W, int32_t H, int32_t tw, int32_t th, int32_t off, int32_t stride,
+int32_t rayn_b200_film_pack_tiles(RaynContext* ctx, int32_t W, int32_t H, int32_t tw, int32_t th, const int32_t* tile_list, int32_t n_tiles,
                                   const RaynFilmPlanes* planes_dev, float* slab_dev) {
-  return pack_unpack(ctx, W, H, tw, th, off, stride, planes_dev, slab_dev, 0);
+  return pack_unpack(ctx, W, H, tw, th, tile_list, n_tiles, planes_dev, slab_dev, 0);
 }
-int32_t rayn_b200_film_unpack_tiles(RaynContext* ctx, int32_t W, int32_t H, int32_t tw, int32_t th, int32_t off, int32_t stride,
+int32_t rayn_b200_film_unpack_tiles(RaynContext* ctx, int32_t W, int32_t H, int32_t tw, int32_t th, const int32_t* tile_list, int32_t n_tiles,
                                     const float* slab_dev, const RaynFilmPlanes* planes_dev) {
-  return pack_unpack(ctx, W, H, tw, th, off, stride, planes_dev, const_cast<float*>(slab_dev), 1);
+  return pack_unpack(ctx, W, H, tw, th, tile_list, n_tiles, planes_dev, const_cast<float*>(slab_dev), 1);
 }
 
 // ---- known-answer entry points ----------------------------------------------------------------------

@@ -1570,13 +1570,12 @@ __global__ void __launch_bounds__(RES_T) k_resolve(const DevFrame fr, const Pass
 // multi-GPU film gather helpers: pack this rank's tiles into a dense slab / unpack a slab.
 // slab layout [k][10][tile_w*tile_h], k = rank-local tile ordinal, pixel order x + y*tile_w.
 // ------------------------------------------------------------------------------------------
-__global__ void k_film_pack(int W, int H, int tile_w, int tile_h, int nty, int n_tiles_total, int off, int stride,
+__global__ void k_film_pack(int W, int H, int tile_w, int tile_h, int nty, const int* __restrict__ tile_list,
                             const float* __restrict__ color, const float* __restrict__ alpha,
                             const float* __restrict__ background, const float* __restrict__ normal, float* __restrict__ slab,
                             int unpack, float* wcolor, float* walpha, float* wbackground, float* wnormal) {
   const int k = blockIdx.x;
-  const int tile_id = off + k * stride;
-  if (tile_id >= n_tiles_total) return;
+  const int tile_id = tile_list[k];
   const int tx = tile_id / nty, ty = tile_id % nty;
   const int x0 = tx * tile_w, y0 = ty * tile_h;
   const int tp = tile_w * tile_h;

@@ -20,31 +20,35 @@ from .film import make_frame_desc, tile_grid
 CHANNEL_FLOATS = (3, 1, 3, 3)  # color, alpha, background, normal (film.rs:103-120)
 
 
-def shard_tiles(n_tiles, rank, world):
-    """Tile indices (film.rs:401-425 order: tile_x * n_tiles_y + tile_y) owned by `rank`."""
-    return list(range(rank, n_tiles, world))
+def shard_tiles(ntx, nty, rank, world, mode="diagonal"):
+    """Ascending tile indices (film.rs:401-425 order: tile_x * n_tiles_y + tile_y) owned by `rank`.
+
+    "diagonal": (tile_x + tile_y) % world == rank — neighbouring tiles in BOTH directions go to
+    different ranks, which balances scenes whose cost is concentrated in the image centre.
+    "index": tile_index % world == rank (what RaynFrameDesc.tile_offset/tile_stride express); with a
+    tile-column height that is a multiple of `world` this hands each rank whole tile rows."""
+    if mode == "index":
+        return list(range(rank, ntx * nty, world))
+    if mode == "diagonal":
+        return [tx * nty + ty for tx in range(ntx) for ty in range(nty) if (tx + ty) % world == rank]
+    raise ValueError(mode)
 
 
-def slab_floats(width, height, tile_size, rank, world):
-    return len(shard_tiles(np.prod(tile_grid(width, height, *tile_size)), rank, world)) * 10 * tile_size[0] * tile_size[1]
-
-
-def max_slab_floats(width, height, tile_size, world):
-    n = int(np.prod(tile_grid(width, height, *tile_size)))
-    return ((n + world - 1) // world) * 10 * tile_size[0] * tile_size[1]
+def max_slab_floats(width, height, tile_size, world, mode="diagonal"):
+    ntx, nty = tile_grid(width, height, *tile_size)
+    return max(len(shard_tiles(ntx, nty, r, world, mode)) for r in range(world)) * 10 * tile_size[0] * tile_size[1]
 
 
 # ---- pack / unpack on plain arrays (host logic; used by the gloo CPU tests and as the spec
-#      the CUDA kernels k_film_pack implement) --------------------------------------------------
-def pack_tiles_numpy(planes, width, height, tile_size, rank, world):
+#      the CUDA kernel k_film_pack implements) ----------------------------------------------------
+def pack_tiles_numpy(planes, width, height, tile_size, tiles):
     tw, th = tile_size
     ntx, nty = tile_grid(width, height, tw, th)
-    mine = shard_tiles(ntx * nty, rank, world)
-    slab = np.zeros((len(mine), 10, th, tw), np.float32)
+    slab = np.zeros((len(tiles), 10, th, tw), np.float32)
     chans = [planes["color"].reshape(height, width, 3), planes["alpha"].reshape(height, width, 1),
              planes["background"].reshape(height, width, 3), planes["normal"].reshape(height, width, 3)]
     full = np.concatenate(chans, axis=2)  # [H, W, 10]
-    for k, idx in enumerate(mine):
+    for k, idx in enumerate(tiles):
         x0, y0 = (idx // nty) * tw, (idx % nty) * th
         x1, y1 = min(x0 + tw, width), min(y0 + th, height)
         if x0 >= width or y0 >= height:
@@ -53,14 +57,13 @@ def pack_tiles_numpy(planes, width, height, tile_size, rank, world):
     return slab.reshape(-1)
 
 
-def unpack_tiles_numpy(slab, planes, width, height, tile_size, rank, world):
+def unpack_tiles_numpy(slab, planes, width, height, tile_size, tiles):
     tw, th = tile_size
     ntx, nty = tile_grid(width, height, tw, th)
-    mine = shard_tiles(ntx * nty, rank, world)
-    slab = np.asarray(slab, np.float32)[: len(mine) * 10 * tw * th].reshape(len(mine), 10, th, tw)
+    slab = np.asarray(slab, np.float32)[: len(tiles) * 10 * tw * th].reshape(len(tiles), 10, th, tw)
     views = [planes["color"].reshape(height, width, 3), planes["alpha"].reshape(height, width, 1),
              planes["background"].reshape(height, width, 3), planes["normal"].reshape(height, width, 3)]
-    for k, idx in enumerate(mine):
+    for k, idx in enumerate(tiles):
         x0, y0 = (idx // nty) * tw, (idx % nty) * th
         x1, y1 = min(x0 + tw, width), min(y0 + th, height)
         if x0 >= width or y0 >= height:
@@ -72,26 +75,27 @@ def unpack_tiles_numpy(slab, planes, width, height, tile_size, rank, world):
             c += nc
 
 
-def gather_film_arrays(planes, width, height, tile_size, rank, world, all_gather):
+def gather_film_arrays(planes, width, height, tile_size, rank, world, all_gather, mode="diagonal"):
     """Backend-agnostic gather: `all_gather(vec) -> list of world vecs` (equal length)."""
-    n = max_slab_floats(width, height, tile_size, world)
-    mine = pack_tiles_numpy(planes, width, height, tile_size, rank, world)
+    ntx, nty = tile_grid(width, height, *tile_size)
+    n = max_slab_floats(width, height, tile_size, world, mode)
+    mine = pack_tiles_numpy(planes, width, height, tile_size, shard_tiles(ntx, nty, rank, world, mode))
     padded = np.zeros(n, np.float32)
     padded[: mine.size] = mine
     for r, slab in enumerate(all_gather(padded)):
         if r != rank:
-            unpack_tiles_numpy(slab, planes, width, height, tile_size, r, world)
+            unpack_tiles_numpy(slab, planes, width, height, tile_size, shard_tiles(ntx, nty, r, world, mode))
     return planes
 
 
 class DistFilm:
     """Device-resident film of one rank + the NCCL gather.  torch is imported lazily."""
 
-    def __init__(self, renderer, width, height, tile_size, rank=0, world=1, group=None):
+    def __init__(self, renderer, width, height, tile_size, rank=0, world=1, group=None, mode="diagonal"):
         import torch
         self.torch = torch
         self.r, self.w, self.h, self.tile = renderer, width, height, tuple(tile_size)
-        self.rank, self.world, self.group = rank, world, group
+        self.rank, self.world, self.group, self.mode = rank, world, group, mode
         dev = torch.device("cuda", renderer.device)
         npx = width * height
         self.store = torch.zeros(10 * npx, dtype=torch.float32, device=dev)
@@ -99,13 +103,17 @@ class DistFilm:
                          "background": self.store[4 * npx: 7 * npx], "normal": self.store[7 * npx:]}
         self.planes = L.RaynFilmPlanes(self.planes_t["color"].data_ptr(), self.planes_t["alpha"].data_ptr(),
                                        self.planes_t["background"].data_ptr(), self.planes_t["normal"].data_ptr(), L.MEM_DEVICE)
+        ntx, nty = tile_grid(width, height, *self.tile)
+        self.shards = [shard_tiles(ntx, nty, r, world, mode) for r in range(world)]
+        self._shard_arrays = [(C.c_int32 * max(len(t), 1))(*t) for t in self.shards]
+        self.tile_list = self.shards[rank] if world > 1 else None
         if world > 1:
-            n = max_slab_floats(width, height, self.tile, world)
+            n = max(len(t) for t in self.shards) * 10 * self.tile[0] * self.tile[1]
             self.slab = torch.zeros(n, dtype=torch.float32, device=dev)
             self.all_slabs = torch.zeros(n * world, dtype=torch.float32, device=dev)
 
     def render(self, frame_desc):
-        """Render this rank's tiles into the device film (frame_desc carries tile_offset/stride)."""
+        """Render this rank's tiles into the device film (frame_desc carries this rank's tile list)."""
         self.r.render(frame_desc, self.planes)
 
     def gather(self):
@@ -115,21 +123,22 @@ class DistFilm:
         torch, lib = self.torch, L.lib()
         import torch.distributed as dist
         tw, th = self.tile
-        L.check(lib.rayn_b200_film_pack_tiles(self.r.ctx, self.w, self.h, tw, th, self.rank, self.world, C.byref(self.planes),
-                                              self.slab.data_ptr()), self.r.ctx)
+        ip = C.POINTER(C.c_int32)
+        L.check(lib.rayn_b200_film_pack_tiles(self.r.ctx, self.w, self.h, tw, th, C.cast(self._shard_arrays[self.rank], ip),
+                                              len(self.shards[self.rank]), C.byref(self.planes), self.slab.data_ptr()), self.r.ctx)
         dist.all_gather_into_tensor(self.all_slabs, self.slab, group=self.group)
         torch.cuda.current_stream().synchronize()
         n = self.slab.numel()
         for r in range(self.world):
             if r == self.rank:
                 continue
-            L.check(lib.rayn_b200_film_unpack_tiles(self.r.ctx, self.w, self.h, tw, th, r, self.world,
+            L.check(lib.rayn_b200_film_unpack_tiles(self.r.ctx, self.w, self.h, tw, th, C.cast(self._shard_arrays[r], ip), len(self.shards[r]),
                                                     self.all_slabs[r * n:(r + 1) * n].data_ptr(), C.byref(self.planes)), self.r.ctx)
 
     def to_host(self):
         return {k: v.cpu().numpy() for k, v in self.planes_t.items()}
 
 
-def device_frame_desc(inputs_dev, width, height, tile_size, samples, integrator, frame, time_range, rank, world, sets):
+def device_frame_desc(inputs_dev, width, height, tile_size, samples, integrator, frame, time_range, sets, tile_list=None):
     ptrs = tuple(t.data_ptr() for t in inputs_dev)
-    return make_frame_desc(width, height, tile_size, samples, integrator, frame, time_range, ptrs, L.MEM_DEVICE, rank, world, sets)
+    return make_frame_desc(width, height, tile_size, samples, integrator, frame, time_range, ptrs, L.MEM_DEVICE, 0, 1, sets, tile_list)

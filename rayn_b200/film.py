@@ -47,7 +47,7 @@ class FrameInputs:
 
 
 def make_frame_desc(width, height, tile_size, samples, integrator, frame, time_range, ptrs, space, tile_offset=0,
-                    tile_stride=1, sets=None):
+                    tile_stride=1, sets=None, tile_list=None):
     f = L.RaynFrameDesc()
     f.width, f.height = width, height
     f.tile_w, f.tile_h = tile_size
@@ -60,6 +60,10 @@ def make_frame_desc(width, height, tile_size, samples, integrator, frame, time_r
     f.samples_1d, f.samples_2d, f.scramble, f.fis_inverse_cdf = ptrs
     f.input_space = space
     f.tile_offset, f.tile_stride = tile_offset, tile_stride
+    if tile_list is not None:  # explicit shard (ascending tile indices); the array must outlive the render call
+        arr = (C.c_int32 * len(tile_list))(*tile_list)
+        f.tile_list, f.n_tile_list = C.cast(arr, C.POINTER(C.c_int32)), len(tile_list)
+        f._keep_tile_list = arr
     return f
 
 
@@ -111,7 +115,7 @@ class Renderer:
         L.check(self._lib.rayn_b200_get_stats(self._ctx, C.byref(s)), self._ctx)
         return s
 
-    def render_host(self, inputs, tile_size, integrator, time_range, tile_offset=0, tile_stride=1):
+    def render_host(self, inputs, tile_size, integrator, time_range, tile_offset=0, tile_stride=1, tile_list=None):
         """Host buffers in, host planes out (H2D + D2H inside the call).  Returns dict of numpy planes."""
         w, h = inputs.width, inputs.height
         planes = {"color": np.zeros(3 * w * h, np.float32), "alpha": np.zeros(w * h, np.float32),
@@ -120,7 +124,7 @@ class Renderer:
                              planes["normal"].ctypes.data, L.MEM_HOST)
         ptrs = tuple(a.ctypes.data for a in inputs.arrays())
         f = make_frame_desc(w, h, tile_size, inputs.samples, integrator, inputs.frame, time_range, ptrs, L.MEM_HOST, tile_offset,
-                            tile_stride, (inputs.sets_1d, inputs.sets_2d))
+                            tile_stride, (inputs.sets_1d, inputs.sets_2d), tile_list)
         self.render(f, p)
         return planes
 

@@ -25,13 +25,15 @@ def _worker(rank, world, port, w, h, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from rayn_b200.dist import gather_film_arrays, pack_tiles_numpy, unpack_tiles_numpy
+        from rayn_b200.dist import gather_film_arrays, pack_tiles_numpy, shard_tiles, unpack_tiles_numpy
+        from rayn_b200.film import tile_grid
         tile = (16, 16)
+        shard = shard_tiles(*tile_grid(w, h, *tile), rank, world)
         rng = np.random.default_rng(42)  # same "full film" on every rank
         full = {"color": rng.random(3 * w * h, dtype=np.float32), "alpha": rng.random(w * h, dtype=np.float32),
                 "background": rng.random(3 * w * h, dtype=np.float32), "normal": rng.random(3 * w * h, dtype=np.float32)}
         mine = {k: np.zeros_like(v) for k, v in full.items()}  # what this rank "rendered": only its own tiles
-        unpack_tiles_numpy(pack_tiles_numpy(full, w, h, tile, rank, world), mine, w, h, tile, rank, world)
+        unpack_tiles_numpy(pack_tiles_numpy(full, w, h, tile, shard), mine, w, h, tile, shard)
 
         def all_gather(vec):
             t = torch.from_numpy(vec)

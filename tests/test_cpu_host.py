@@ -101,15 +101,31 @@ def test_pack_unpack_roundtrip_with_clipped_tiles():
     rng = np.random.default_rng(0)
     full = {"color": rng.random(3 * w * h, dtype=np.float32), "alpha": rng.random(w * h, dtype=np.float32),
             "background": rng.random(3 * w * h, dtype=np.float32), "normal": rng.random(3 * w * h, dtype=np.float32)}
-    out = {k: np.zeros_like(v) for k, v in full.items()}
     ntx, nty = tile_grid(w, h, *tile)
-    assert sorted(sum((shard_tiles(ntx * nty, r, 3) for r in range(3)), [])) == list(range(ntx * nty))
-    for r in range(3):
-        slab = pack_tiles_numpy(full, w, h, tile, r, 3)
-        assert slab.size <= max_slab_floats(w, h, tile, 3)
-        unpack_tiles_numpy(slab, out, w, h, tile, r, 3)
-    for k in full:
-        assert np.array_equal(out[k], full[k])
+    for mode in ("diagonal", "index"):
+        out = {k: np.zeros_like(v) for k, v in full.items()}
+        shards = [shard_tiles(ntx, nty, r, 3, mode) for r in range(3)]
+        assert sorted(sum(shards, [])) == list(range(ntx * nty))  # a partition of the tile grid
+        assert all(s == sorted(s) for s in shards)
+        for r in range(3):
+            slab = pack_tiles_numpy(full, w, h, tile, shards[r])
+            assert slab.size <= max_slab_floats(w, h, tile, 3, mode)
+            unpack_tiles_numpy(slab, out, w, h, tile, shards[r])
+        for k in full:
+            assert np.array_equal(out[k], full[k])
+
+
+def test_diagonal_interleave_balances_rows_and_columns():
+    ntx, nty = tile_grid(1024, 1024, 16, 16)
+    for world in (2, 4, 8):
+        sizes = [len(shard_tiles(ntx, nty, r, world)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 1
+        centre_counts = []
+        for r in range(world):
+            t = np.array(shard_tiles(ntx, nty, r, world))
+            rows, cols = t % nty, t // nty
+            centre_counts.append(int(((np.abs(rows - nty / 2) < 8) & (np.abs(cols - ntx / 2) < 8)).sum()))  # where the fractal is
+        assert sum(centre_counts) == 15 * 15 and max(centre_counts) - min(centre_counts) <= 2
 
 
 def test_gather_with_a_fake_collective():
@@ -117,16 +133,18 @@ def test_gather_with_a_fake_collective():
     rng = np.random.default_rng(1)
     full = {"color": rng.random(3 * w * h, dtype=np.float32), "alpha": rng.random(w * h, dtype=np.float32),
             "background": rng.random(3 * w * h, dtype=np.float32), "normal": rng.random(3 * w * h, dtype=np.float32)}
+    ntx, nty = tile_grid(w, h, *tile)
+    shards = [shard_tiles(ntx, nty, r, world) for r in range(world)]
     parts = []
     for r in range(world):
         mine = {k: np.zeros_like(v) for k, v in full.items()}
-        unpack_tiles_numpy(pack_tiles_numpy(full, w, h, tile, r, world), mine, w, h, tile, r, world)
+        unpack_tiles_numpy(pack_tiles_numpy(full, w, h, tile, shards[r]), mine, w, h, tile, shards[r])
         parts.append(mine)
     n = max_slab_floats(w, h, tile, world)
     slabs = []
     for r in range(world):
         s = np.zeros(n, np.float32)
-        p = pack_tiles_numpy(parts[r], w, h, tile, r, world)
+        p = pack_tiles_numpy(parts[r], w, h, tile, shards[r])
         s[:p.size] = p
         slabs.append(s)
     for r in range(world):

@@ -38,8 +38,8 @@ def _worker(rank, world, port, q):
         r = Renderer(rank)
         r.upload_scene(c["world"], c["camera"])
         film = DistFilm(r, 176, 104, (16, 16), rank, world)
-        fd = device_frame_desc(inputs_dev, 176, 104, (16, 16), c["samples"], c["integrator"], 1, configs.frame_time_range(1), rank, world,
-                               (inp.sets_1d, inp.sets_2d))
+        fd = device_frame_desc(inputs_dev, 176, 104, (16, 16), c["samples"], c["integrator"], 1, configs.frame_time_range(1),
+                               (inp.sets_1d, inp.sets_2d), film.tile_list)
         film.render(fd)
         film.gather()
         got = film.to_host()

@@ -201,8 +201,15 @@ def test_pass_size_and_sharding_do_not_change_the_film(oracle):
     try:
         r.upload_scene(c["world"], c["camera"])
         acc = {ch: np.zeros_like(full[ch]) for ch in CH}
+        from rayn_b200.dist import shard_tiles
+        from rayn_b200.film import tile_grid
+        ntx, nty = tile_grid(160, 96, 16, 16)
         for rank in range(3):
-            part = r.render_host(inp, (16, 16), c["integrator"], TR, tile_offset=rank, tile_stride=3)
+            if rank == 0:  # offset/stride form of the ABI ...
+                part = r.render_host(inp, (16, 16), c["integrator"], TR, tile_offset=rank, tile_stride=3)
+                r.render_host(inp, (16, 16), c["integrator"], TR, tile_list=shard_tiles(ntx, nty, rank, 3, "index"))
+            else:          # ... and the explicit tile-list form give the same shard
+                part = r.render_host(inp, (16, 16), c["integrator"], TR, tile_list=shard_tiles(ntx, nty, rank, 3, "index"))
             for ch in CH:
                 assert not (np.logical_and(acc[ch] != 0, part[ch] != 0)).any()
                 acc[ch] += part[ch]
