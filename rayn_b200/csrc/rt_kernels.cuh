@@ -157,20 +157,21 @@ __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ DevScene
 // tile's live rays by object id, every bin padded to a multiple of 4 with -1.  One CTA per
 // tile; chunks of BIN_T rays; per-warp __match_any_sync ranks + cross-warp offsets in smem.
 // ------------------------------------------------------------------------------------------
-#define BIN_T 256
+#define BIN_T 1024
 __global__ void __launch_bounds__(BIN_T) k_bin(const PassBufs pb, const int n_hit) {
   const int ts = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = BIN_T / 32;
   const int n = pb.n_live[ts];
   __shared__ int cnt[RAYN_MAX_HITABLES];
   __shared__ int start[RAYN_MAX_HITABLES + 1];
-  __shared__ int running[RAYN_MAX_HITABLES];
-  __shared__ int wcnt[BIN_T / 32][RAYN_MAX_HITABLES];
+  __shared__ int running[2][RAYN_MAX_HITABLES];
+  __shared__ int wcnt[2][NW][RAYN_MAX_HITABLES];
   const int* __restrict__ qk = pb.q_key + (size_t)ts * pb.R;
   const int* __restrict__ ql = pb.q_live + (size_t)ts * pb.R;
   int* __restrict__ qs = pb.q_shade + (size_t)ts * pb.QS;
   if (tid < RAYN_MAX_HITABLES) cnt[tid] = 0;
   __syncthreads();
-  for (int base = 0; base < n; base += BIN_T) {
+  for (int base = 0; base < n; base += BIN_T) {  // pass A: per-object counts
     const int i = base + tid;
     const int key = i < n ? qk[i] : -1;
     const unsigned m = __match_any_sync(0xffffffffu, key);
@@ -181,36 +182,37 @@ __global__ void __launch_bounds__(BIN_T) k_bin(const PassBufs pb, const int n_hi
     int off = 0;
     for (int o = 0; o < n_hit; ++o) {
       start[o] = off;
-      running[o] = off;
-      off += (cnt[o] + 3) & ~3;
+      running[0][o] = off;
+      off += (cnt[o] + 3) & ~3;  // every bin padded to a multiple of 4 (hitable.rs:100-111)
     }
     start[n_hit] = off;
     pb.n_slots[ts] = off;
   }
   __syncthreads();
   if (tid <= n_hit) pb.bin_start[ts * (RAYN_MAX_HITABLES + 1) + tid] = start[tid];
-  for (int base = 0; base < n; base += BIN_T) {
+  // pass B: stable scatter, ONE barrier per 1024-ray chunk (double-buffered warp counts and bin cursors)
+  int buf = 0;
+  for (int base = 0; base < n; base += BIN_T, buf ^= 1) {
     const int i = base + tid;
     const int key = i < n ? qk[i] : -1;
     const int id = i < n ? ql[i] : -1;
-    for (int k = tid; k < (BIN_T / 32) * RAYN_MAX_HITABLES; k += BIN_T) (&wcnt[0][0])[k] = 0;
-    __syncthreads();
-    const unsigned m = __match_any_sync(0xffffffffu, key);
-    const int rank = __popc(m & ((1u << lane) - 1));
-    if (key >= 0 && rank == 0) wcnt[warp][key] = __popc(m);
+    unsigned mine = 0;
+    for (int k = 0; k < n_hit; ++k) {
+      const unsigned b = __ballot_sync(0xffffffffu, key == k);
+      if (key == k) mine = b;
+      if (lane == k) wcnt[buf][warp][k] = __popc(b);
+    }
     __syncthreads();
     if (key >= 0) {
-      int off = running[key];
-      for (int w = 0; w < warp; ++w) off += wcnt[w][key];
-      qs[off + rank] = id;
+      int off = running[buf][key] + __popc(mine & ((1u << lane) - 1));
+      for (int w = 0; w < warp; ++w) off += wcnt[buf][w][key];
+      qs[off] = id;
     }
-    __syncthreads();
     if (tid < n_hit) {
-      int tot = 0;
-      for (int w = 0; w < BIN_T / 32; ++w) tot += wcnt[w][tid];
-      running[tid] += tot;
+      int tot = running[buf][tid];
+      for (int w = 0; w < NW; ++w) tot += wcnt[buf][w][tid];
+      running[buf ^ 1][tid] = tot;
     }
-    __syncthreads();
   }
   if (tid < n_hit)
     for (int k = start[tid] + cnt[tid]; k < start[tid + 1]; ++k) qs[k] = -1;  // Ray::new_invalid padding
@@ -1421,35 +1423,30 @@ __global__ void __launch_bounds__(128, 4) k_shade_post(const __grid_constant__ D
 // in shared memory, running tile offset.  (Padding the survivors to x4, film.rs:608-610, has
 // no observable effect: add_hits drops invalid lanes, hitable.rs:204.)
 // ------------------------------------------------------------------------------------------
-#define CMP_T 256
+#define CMP_T 1024
 __global__ void __launch_bounds__(CMP_T) k_compact(const PassBufs pb) {
   const int ts = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = CMP_T / 32;
   const int n = pb.n_slots[ts];
   const int* __restrict__ qs = pb.q_shade + (size_t)ts * pb.QS;
   int* __restrict__ ql = pb.q_live + (size_t)ts * pb.R;
-  __shared__ int wtot[CMP_T / 32];
-  __shared__ int running;
-  if (tid == 0) running = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += CMP_T) {
+  __shared__ int wtot[2][NW];
+  __shared__ int running[2];
+  if (tid == 0) running[0] = 0;
+  int buf = 0;
+  for (int base = 0; base < n; base += CMP_T, buf ^= 1) {  // one barrier per 1024-slot chunk
     const int i = base + tid;
     const int id = i < n ? qs[i] : -1;
     const unsigned b = __ballot_sync(0xffffffffu, id >= 0);
-    const int rank = __popc(b & ((1u << lane) - 1));
-    if (lane == 0) wtot[warp] = __popc(b);
+    if (lane == 0) wtot[buf][warp] = __popc(b);
     __syncthreads();
-    int off = running;
-    for (int w = 0; w < warp; ++w) off += wtot[w];
-    if (id >= 0) ql[off + rank] = id;
-    __syncthreads();
-    if (tid == 0) {
-      int tot = 0;
-      for (int w = 0; w < CMP_T / 32; ++w) tot += wtot[w];
-      running += tot;
-    }
-    __syncthreads();
+    int off = running[buf] + __popc(b & ((1u << lane) - 1));
+    for (int w = 0; w < warp; ++w) off += wtot[buf][w];
+    if (id >= 0) ql[off] = id;
+    if (tid == CMP_T - 1) running[buf ^ 1] = off + (id >= 0 ? 1 : 0);  // last thread's end offset = new total
   }
-  if (tid == 0) pb.n_live[ts] = running;
+  __syncthreads();
+  if (tid == 0) pb.n_live[ts] = running[buf];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1490,7 +1487,7 @@ RT_D void sort_if_needed(uint32_t* key, int* val, int np) {
   if (__syncthreads_or(bad)) bitonic_sort(key, val, np);
 }
 
-static inline size_t resolve_smem_bytes(int np) { return (size_t)np * (2 * 4 + 7 * 4 + 4); }
+static inline size_t resolve_smem_bytes(int np) { return (size_t)np * (2 * 4 + 6 * 4 + 2 * 4 + 3 * 4); }
 
 __global__ void __launch_bounds__(RES_T) k_resolve(const DevFrame fr, const PassBufs pb, float* __restrict__ color,
                                                    float* __restrict__ alpha, float* __restrict__ background,
@@ -1530,16 +1527,29 @@ __global__ void __launch_bounds__(RES_T) k_resolve(const DevFrame fr, const Pass
   __syncthreads();
   // ---- order A: depth-0 receives_light hits by slot -> WorldNormal, Alpha (integrator.rs:161-169)
   sort_if_needed(key, val, np);
-  if (tid < 4) {
+  float* g0s = reinterpret_cast<float*>(tw + np);  // 3 x np scratch: channel values gathered in summation order
+  float *g1s = g0s + np, *g2s = g1s + np;
+  for (int i = tid; i < np; i += RES_T) {
+    const bool on = key[i] != 0xffffffffu;
+    const int v = val[i];
+    g0s[i] = on ? nx[v] : 0.0f;
+    g1s[i] = on ? ny[v] : 0.0f;
+    g2s[i] = on ? nz[v] : 0.0f;
+    val[i] = on ? 1 : 0;  // Alpha(1.0) per sample
+  }
+  __syncthreads();
+  if (tid < 4) {  // strictly sequential float sums, in the reference's order; + 0.0f entries are exact no-ops
+    const float* src = tid == 0 ? g0s : tid == 1 ? g1s : g2s;
     float acc = 0.0f;
-    for (int i = 0; i < np && key[i] != 0xffffffffu; ++i) {
-      const int v = val[i];
-      acc += tid == 0 ? nx[v] : tid == 1 ? ny[v] : tid == 2 ? nz[v] : 1.0f;
-    }
-    if (tid < 3)
+    if (tid < 3) {
+#pragma unroll 8
+      for (int i = 0; i < np; ++i) acc += src[i];
       normal[3 * pix + tid] = acc / div;
-    else
+    } else {
+#pragma unroll 8
+      for (int i = 0; i < np; ++i) acc += (float)val[i];
       alpha[pix] = acc / div;
+    }
   }
   __syncthreads();
   // ---- order B: terminated paths by (depth, slot) -> Color / Background (integrator.rs:178-203)
@@ -1550,15 +1560,30 @@ __global__ void __launch_bounds__(RES_T) k_resolve(const DevFrame fr, const Pass
   }
   __syncthreads();
   sort_if_needed(key, val, np);
+  // colour in g0s..g2s, background in nx..nz (no longer needed), both in summation order
+  float b0, b1, b2, c0, c1, c2;
+  for (int base = 0; base < np; base += RES_T) {
+    const int i = base + tid;
+    b0 = b1 = b2 = c0 = c1 = c2 = 0.0f;
+    if (i < np && key[i] != 0xffffffffu) {
+      const int v = val[i];
+      const uint32_t kind = tw[v] >> 30;
+      if (kind == TERM_COLOR) c0 = rx[v], c1 = ry[v], c2 = rz[v];
+      if (kind == TERM_BACKGROUND) b0 = rx[v], b1 = ry[v], b2 = rz[v];
+    }
+    __syncthreads();  // all reads of this chunk done before nx..nz / g*s of the same indices are overwritten
+    if (i < np) {
+      g0s[i] = c0, g1s[i] = c1, g2s[i] = c2;
+      nx[i] = b0, ny[i] = b1, nz[i] = b2;
+    }
+  }
+  __syncthreads();
   if (tid < 6) {
     const int ch = tid % 3;
-    const uint32_t want = tid < 3 ? TERM_COLOR : TERM_BACKGROUND;
-    const float* src = ch == 0 ? rx : ch == 1 ? ry : rz;
+    const float* src = tid < 3 ? (ch == 0 ? g0s : ch == 1 ? g1s : g2s) : (ch == 0 ? nx : ch == 1 ? ny : nz);
     float acc = 0.0f;
-    for (int i = 0; i < np && key[i] != 0xffffffffu; ++i) {
-      const int v = val[i];
-      if ((tw[v] >> 30) == want) acc += src[v];
-    }
+#pragma unroll 8
+    for (int i = 0; i < np; ++i) acc += src[i];
     if (tid < 3)
       color[3 * pix + ch] = acc / div;
     else
