@@ -310,3 +310,41 @@ def test_cpp_host_renders_the_same_film_as_the_python_host(renderer, tmp_path):
     got = {"color": raw[:3 * npx], "alpha": raw[3 * npx:4 * npx], "background": raw[4 * npx:7 * npx], "normal": raw[7 * npx:]}
     for ch in CH:
         assert_bit_equal(got[ch], g[ch], f"C++ host {ch}")
+
+
+# ---- BASELINE full sizes: sampled bit-exact parity + properties ---------------------------------
+@pytest.mark.parametrize("n,k", [(2, 409), (3, 1361)])
+def test_full_size_config_tile_sample_matches_oracle(oracle, n, k):
+    """The GPU renders BASELINE config n at its FULL size (cfg2: 1024x1024x128spp, cfg3: 1920x1080x512spp);
+    the oracle renders every k-th tile of the same frame (the CPU cannot do the whole frame in test time).
+    Tiles are independent (film.rs:439-627), so those tiles must agree bit for bit."""
+    c = configs.baseline_config(n)
+    w, h = c["res"]
+    inp = FrameInputs(w, h, c["samples"], c["integrator"])
+    r = Renderer(0)
+    try:
+        r.upload_scene(c["world"], c["camera"])
+        g = r.render_host(inp, (16, 16), c["integrator"], TR)
+        st = r.stats()
+    finally:
+        r.close()
+    assert st.paths == w * h * c["spp"]
+    o, info = oracle.render(c["world"], c["camera"], inp, (16, 16), c["integrator"], TR, subsample_k=k)
+    assert 4 <= info["tiles"] <= 12
+    from rayn_b200.film import tile_grid
+    ntx, nty = tile_grid(w, h, 16, 16)
+    mask = np.zeros((h, w), bool)
+    for idx in range(0, ntx * nty, k):
+        x0, y0 = (idx // nty) * 16, (idx % nty) * 16
+        mask[y0:y0 + 16, x0:x0 + 16] = True
+    m = mask.reshape(-1)
+    assert m.sum() >= 4 * 128
+    for ch in CH:
+        a = g[ch].reshape(w * h, -1)[m]
+        b = o[ch].reshape(w * h, -1)[m]
+        assert_bit_equal(a, b, f"full-size cfg{n} {ch}")
+    # properties of the whole frame
+    assert np.isfinite(g["color"]).all() and (g["color"] >= 0).all() and (g["background"] >= 0).all()
+    assert g["alpha"].min() >= 0 and g["alpha"].max() <= 1.0
+    covered = (g["alpha"] > 0) | (g["background"].reshape(-1, 3).sum(1) > 0)
+    assert covered.mean() > 0.999  # every camera ray ends on the sky sphere or the fractal
