@@ -317,6 +317,16 @@ def main():
                 "fp32_frac_extend": per_kernel["extend"].get("fp32_tflops_algorithmic", 0.0) / FP32_PEAK_TFLOPS,
                 "fp32_frac_shadow": per_kernel[sh_key].get("fp32_tflops_algorithmic", 0.0) / FP32_PEAK_TFLOPS,
                 "launches_of_kernel_per_step": klaunch.get(dom, 0)}
+    # measured DRAM traffic of the dominant kernel from the committed ncu capture (per launch, like `achieved`)
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and args.config == 2 and world == 1 and args.flags == 0:
+        tj = json.load(open(tpath))
+        key = {"extend": "k_extend_march", "shadow": "k_shadow"}.get(dom)
+        if key in tj:
+            roofline["traffic"] = tj[key]["dram_bytes_per_launch"][0]
+            roofline["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of the depth-0 launch of pass 2 (50.3 M rays) from "
+                                        + tj[key]["source"] + "; algorithmic bytes of that launch: "
+                                        + str(tj[key].get("algorithmic_bytes_per_launch", [None])[0]))
     rt.close()
     del filmt
 
