@@ -306,7 +306,7 @@ def main():
         per_kernel["shade_pre"]["lanes"] = int(ts.shade_lanes)
         per_kernel["shade_pre"]["hbm_gbs_algorithmic"] = ts.shade_lanes * ALG_BYTES_SHADE / max(shade_s, 1e-12) / 1e9
     dom = max(kms, key=kms.get) if kms else "extend"
-    dom_name = {"extend": "k_extend3 (closest-hit sphere-march)", "shadow": "k_shadow (occlusion sphere-march)",
+    dom_name = {"extend": "k_extend_march (closest-hit sphere-march)", "shadow": "k_shadow (occlusion sphere-march)",
                 "shade_pre": "k_shade_pre", "shade_post": "k_shade_post"}.get(dom, dom)
     achieved = per_kernel[dom].get("hbm_gbs_algorithmic", 0.0)
     roofline = {"kernel": dom_name, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,

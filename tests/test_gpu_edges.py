@@ -1,0 +1,130 @@
+"""Edge cases of the path (the reference has no tests of its own; these are the ragged / empty /
+extreme shapes its code can be driven into), each bit-exact vs the oracle."""
+import numpy as np
+import pytest
+
+from rayn_b200 import _lib as L
+from rayn_b200 import (BoxFold, CameraStore, Dielectric, Emissive, HitableStore, Lambertian, MandelBox, Mandelbulb, MaterialStore,
+                       PathTracingIntegrator, PinholeCamera, Sky, Sphere, SphereFold, SphereLight, Srgb, TracedSDF, Vec3, VolumeParams,
+                       World, configs)
+from rayn_b200.film import FrameInputs, Renderer
+
+from helpers import CH, assert_bit_equal, small_config
+
+pytestmark = pytest.mark.gpu
+TR = configs.frame_time_range(1)
+
+
+def _both(renderer, oracle, world, cam, res, samples, mb, tile=(16, 16)):
+    integ = PathTracingIntegrator(mb, 2)
+    inp = FrameInputs(res[0], res[1], samples, integ)
+    renderer.upload_scene(world, cam)
+    g = renderer.render_host(inp, tile, integ, TR)
+    o, info = oracle.render(world, cam, inp, tile, integ, TR)
+    for ch in CH:
+        assert_bit_equal(g[ch], o[ch], ch)
+    return g, info
+
+
+def _world(hitables, lights, materials, res, volume=VolumeParams(None, None)):
+    cams = CameraStore()
+    cam = cams.add_camera(PinholeCamera(res, 60.0, Vec3(-0.45, 0.2, 2.0) * 2.25, Vec3(0.0, 0.0, 0.0), Vec3(0.0, 1.0, 0.0)))
+    return cam, World(hitables, lights, materials, cams, volume)
+
+
+def test_image_smaller_than_a_tile_and_minimal_spp(renderer, oracle):
+    c = configs.baseline_config(3, res=(5, 3), samples=1, max_bounces=2)
+    g, info = _both(renderer, oracle, c["world"], c["camera"], (5, 3), 1, 2)
+    assert info["tiles"] == 0 or g["alpha"].size == 15  # 5 % 16 = 5 < 8 -> the reference renders ZERO tiles (film.rs:399-404)
+    c = configs.baseline_config(3, res=(9, 12), samples=1, max_bounces=2)  # 9 % 16 = 9 >= 8 -> one clipped tile
+    g, info = _both(renderer, oracle, c["world"], c["camera"], (9, 12), 1, 2)
+    assert info["tiles"] == 1 and float(g["color"].sum() + g["background"].sum()) > 0
+
+
+@pytest.mark.parametrize("tile", [(8, 8), (32, 16), (16, 4)])
+def test_other_tile_sizes(renderer, oracle, tile):
+    c = configs.baseline_config(3, res=(64, 48), samples=1, max_bounces=2)
+    _both(renderer, oracle, c["world"], c["camera"], (64, 48), 1, 2, tile)
+
+
+def test_zero_bounces_and_no_lights(renderer, oracle):
+    c = configs.baseline_config(3, res=(32, 32), samples=1, max_bounces=0)  # every path ends at depth 0 (integrator.rs:178)
+    _both(renderer, oracle, c["world"], c["camera"], (32, 32), 1, 0)
+    materials, hitables = MaterialStore(), HitableStore()
+    sky = materials.add_material(Sky(Srgb(0.3, 0.4, 0.6), Srgb(0.2, 0.3, 0.6) * 0.05))
+    grey = materials.add_material(Lambertian(Srgb(0.5, 0.4, 0.3)))
+    hitables.push(Sphere(Vec3(0, 0, 0), 100.0, sky))
+    hitables.push(Sphere(Vec3(0, 0, 0), 1.0, grey))
+    cam, world = _world(hitables, [], materials, (32, 32))  # world.lights.len() == 0: NEE skipped (integrator.rs:73)
+    g, _ = _both(renderer, oracle, world, cam, (32, 32), 2, 3)
+    assert float(g["color"].sum()) > 0  # sky light arrives through Lambertian bounces
+
+
+def test_sky_only_scene_all_paths_end_at_depth_zero(renderer, oracle):
+    materials, hitables = MaterialStore(), HitableStore()
+    sky = materials.add_material(Sky(Srgb(0.3, 0.4, 0.6), Srgb(0.2, 0.3, 0.6) * 0.05))
+    hitables.push(Sphere(Vec3(0, 0, 0), 100.0, sky))
+    cam, world = _world(hitables, [SphereLight(Vec3(1, 1, 1), 0.1, Srgb(1, 1, 1))], materials, (48, 32))
+    g, _ = _both(renderer, oracle, world, cam, (48, 32), 2, 3)
+    assert g["color"].sum() == 0 and g["alpha"].sum() == 0 and (g["background"] > 0).all()
+
+
+def test_rays_that_hit_nothing_are_dropped_but_counted(renderer, oracle):
+    """No sky sphere: camera rays that miss everything vanish, yet the divisor stays spp."""
+    materials, hitables = MaterialStore(), HitableStore()
+    em = materials.add_material(Emissive.new_splat(Srgb(2.0, 1.0, 0.5)))
+    hitables.push(Sphere(Vec3(0, 0, 0), 1.0, em))
+    cam, world = _world(hitables, [], materials, (32, 32))
+    g, _ = _both(renderer, oracle, world, cam, (32, 32), 2, 2)
+    img = g["background"].reshape(32, 32, 3)
+    assert img[0, 0].sum() == 0 and img[16, 16, 0] > 0
+    edge = img[:, :, 0][(img[:, :, 0] > 0) & (img[:, :, 0] < 2.0)]
+    assert edge.size > 0  # partially covered pixels are darker: lost samples still divide
+
+
+def test_two_sdfs_and_volume(renderer, oracle):
+    """Two TracedSDF hitables (Mandelbox then Mandelbulb) around analytic spheres: exercises the per-SDF march
+    kernels in fold order (hitable.rs:177-198) and shadow segments per SDF hitable."""
+    materials, hitables, lights = MaterialStore(), HitableStore(), []
+    sky = materials.add_material(Sky(Srgb(0.3, 0.4, 0.6), Srgb(0.2, 0.3, 0.6) * 0.05))
+    grey = materials.add_material(Dielectric.new_remap(Srgb(0.2, 0.2, 0.2), 0.6))
+    red = materials.add_material(Lambertian(Srgb(0.6, 0.2, 0.2)))
+    hitables.push(TracedSDF(Mandelbulb(6, 8, 2.0), red))
+    hitables.push(Sphere(Vec3(0, 0, 0), 100.0, sky))
+    hitables.push(TracedSDF(MandelBox(8, BoxFold(1.0), SphereFold(0.5, 1.0), -2.0), grey))
+    hitables.push(Sphere(Vec3(0.0, 1.6, 0.0), 0.3, red))
+    lights.append(SphereLight(Vec3(2.5, 2.5, 2.5), 0.2, Srgb(1, 1, 1) * 60.0))
+    lights.append(SphereLight(Vec3(-2.5, 1.0, 2.5), 0.2, Srgb(0.5, 0.7, 1.0) * 60.0))
+    cam, world = _world(hitables, lights, materials, (40, 40), VolumeParams(0.25, 0.035))
+    g, info = _both(renderer, oracle, world, cam, (40, 40), 1, 3)
+    assert info["sdf_evals_extend"] > 0 and float(g["color"].sum()) > 0
+
+
+def test_scattering_without_extinction_and_vice_versa(renderer, oracle):
+    c = configs.baseline_config(4, res=(32, 32), samples=1, max_bounces=2)
+    for vol in (VolumeParams(0.25, None), VolumeParams(None, 0.035)):  # Option<f32> pairs are independent (volume.rs:2-5)
+        c["world"].volume_params = vol
+        _both(renderer, oracle, c["world"], c["camera"], (32, 32), 1, 2)
+
+
+def test_limits_are_reported_not_crashed():
+    r = Renderer(0)
+    try:
+        c, inp = small_config(1, (16, 16), 1, 1)
+        r.upload_scene(c["world"], c["camera"])
+        big = PathTracingIntegrator(1, 2)
+        huge = FrameInputs(16, 16, 1100, big)  # 16*16*4400 spp > 2^20 slot keys
+        with pytest.raises(L.RaynError) as e:
+            r.render_host(huge, (16, 16), big, TR)
+        assert e.value.code == L.RAYN_ERR_UNSUPPORTED
+        with pytest.raises(L.RaynError) as e:
+            r.render_host(inp, (16, 16), big, TR, tile_list=[3, 1])  # not ascending
+        assert e.value.code == L.RAYN_ERR_INVALID_ARG
+        d, _ = c["world"].flatten(c["camera"])
+        d.hitables[1].kind = L.HITABLE_MANDELBULB
+        d.hitables[1].bulb_power = 5
+        with pytest.raises(L.RaynError) as e:
+            r.upload_scene_desc(d)
+        assert e.value.code == L.RAYN_ERR_UNSUPPORTED
+    finally:
+        r.close()
