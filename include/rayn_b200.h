@@ -264,6 +264,23 @@ int32_t rayn_b200_film_unpack_tiles(RaynContext* ctx, int32_t width, int32_t hei
                                     int32_t tile_h, const int32_t* tile_list, int32_t n_tiles,
                                     const float* slab_dev, const RaynFilmPlanes* planes_dev);
 
+/* ---- film post-process: the per-pixel arithmetic of Film::save_to (src/film.rs:205-377) -----
+ * (the step AFTER the path; PNG encoding itself stays host I/O.)
+ * Writes the pixel buffer the reference hands to the `image` crate: rows top to bottom
+ * (y flipped, film.rs:236), 8 bits per sample, `(v*255).min(255).max(0) as u8`.             */
+typedef enum RaynPostMode {
+  RAYN_POST_COLOR_PLUS_BACKGROUND = 0, /* RGB8  (col+bg).saturated().gamma_corrected(2.2)  film.rs:253-274 */
+  RAYN_POST_COLOR_ALPHA = 1,           /* RGBA8 col.saturated().gamma_corrected(2.2), a    film.rs:230-252 */
+  RAYN_POST_COLOR_ONLY = 2,            /* RGB8  col.gamma_corrected(2.2)  (no saturate)    film.rs:275-293 */
+  RAYN_POST_BACKGROUND = 3,            /* RGB8  bg.saturated().gamma_corrected(2.2)        film.rs:300-325 */
+  RAYN_POST_WORLD_NORMAL = 4,          /* RGB8  n*0.5 + 0.5                                film.rs:326-350 */
+  RAYN_POST_ALPHA = 5                  /* L8    a                                          film.rs:351-372 */
+} RaynPostMode;
+/* planes->space says where the float planes live; out_space where `out` lives (RaynMemSpace).
+ * out holds width*height*{3,4,3,3,3,1} bytes.                                                */
+int32_t rayn_b200_film_postprocess(RaynContext* ctx, int32_t mode, int32_t width, int32_t height,
+                                   const RaynFilmPlanes* planes, uint8_t* out, int32_t out_space);
+
 /* ---- host-side input builders (pure CPU; stand in for crates the Rust host owns) ----
  * quasi-rd R_d tables (sampler.rs:18-37), rand SmallRng scramble (film.rs:460-461),
  * FilterImportanceSampler::new(BlackmanHarris) (filter.rs:13-49,196-218).               */

@@ -42,6 +42,7 @@ def lib():
                                               C.c_float, C.c_int32, fp]
         l.rayn_oracle_kat_occluded.argtypes = [C.POINTER(L.RaynSceneDesc), C.c_int64, fp, fp, fp]
         l.rayn_oracle_kat_closest_hit.argtypes = [C.POINTER(L.RaynSceneDesc), C.c_int32, C.c_int64, fp, fp, fp, C.POINTER(C.c_int32)]
+        l.rayn_oracle_film_postprocess.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(L.RaynFilmPlanes), C.c_void_p]
         if l.rayn_oracle_selfcheck() != 0:
             raise RuntimeError("oracle was built with FP contraction on: rebuild with -ffp-contract=off")
         _lib = l
@@ -125,3 +126,12 @@ def kat_closest_hit(scene_desc, depth, origins, dirs):
     obj = np.empty(len(o), np.int32)
     lib().rayn_oracle_kat_closest_hit(C.byref(scene_desc), depth, len(o), _f(o), _f(d), _f(t), obj.ctypes.data_as(C.POINTER(C.c_int32)))
     return t, obj
+
+
+def film_postprocess(mode, width, height, planes):
+    """CPU restatement of Film::save_to's pixel arithmetic (film.rs:205-377) -> uint8 array [H, W, bpp]."""
+    p = L.RaynFilmPlanes(planes["color"].ctypes.data, planes["alpha"].ctypes.data, planes["background"].ctypes.data,
+                         planes["normal"].ctypes.data, L.MEM_HOST)
+    out = np.zeros((height, width, L.POST_BYTES[mode]), np.uint8)
+    lib().rayn_oracle_film_postprocess(mode, width, height, C.byref(p), out.ctypes.data)
+    return out

@@ -1113,6 +1113,36 @@ int32_t rayn_oracle_render_frame(const RaynSceneDesc* scene, const RaynFrameDesc
   return RAYN_OK;
 }
 
+// Film::save_to per-pixel arithmetic (film.rs:205-377), scalar f32 like the reference.
+static inline float o_saturate(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }                 // spectrum.rs:35-40 (f32::max/min: NaN loses)
+static inline float o_gamma(float x) { return dm::pow(x, 1.0f / 2.2f); }                         // spectrum.rs:30-32
+static inline uint8_t o_u8(float v) {                                                            // `(v*255.0).min(255.0).max(0.0) as u8`
+  float a = fmaxf(fminf(v * 255.0f, 255.0f), 0.0f);
+  return (uint8_t)(int)a;
+}
+int32_t rayn_oracle_film_postprocess(int32_t mode, int32_t W, int32_t H, const RaynFilmPlanes* pl, uint8_t* out) {
+  const int bpp = mode == RAYN_POST_COLOR_ALPHA ? 4 : (mode == RAYN_POST_ALPHA ? 1 : 3);
+  for (int y = 0; y < H; ++y)
+    for (int x = 0; x < W; ++x) {
+      const size_t idx = (size_t)x + (size_t)(H - 1 - y) * W;  // film.rs:236
+      uint8_t* d = out + ((size_t)x + (size_t)y * W) * bpp;
+      for (int c = 0; c < 3 && mode != RAYN_POST_ALPHA; ++c) {
+        float v;
+        switch (mode) {
+          case RAYN_POST_COLOR_PLUS_BACKGROUND: v = o_gamma(o_saturate(pl->color[3 * idx + c] + pl->background[3 * idx + c])); break;
+          case RAYN_POST_COLOR_ALPHA: v = o_gamma(o_saturate(pl->color[3 * idx + c])); break;
+          case RAYN_POST_COLOR_ONLY: v = o_gamma(pl->color[3 * idx + c]); break;
+          case RAYN_POST_BACKGROUND: v = o_gamma(o_saturate(pl->background[3 * idx + c])); break;
+          default: v = pl->normal[3 * idx + c] * 0.5f + 0.5f;
+        }
+        d[c] = o_u8(v);
+      }
+      if (mode == RAYN_POST_COLOR_ALPHA) d[3] = o_u8(pl->alpha[idx]);
+      if (mode == RAYN_POST_ALPHA) d[0] = o_u8(pl->alpha[idx]);
+    }
+  return RAYN_OK;
+}
+
 int32_t rayn_oracle_kat_detmath(int32_t op, int64_t n, const float* a, const float* b, float* out) {
   for (int64_t i = 0; i < n; ++i) {
     float s, c;

@@ -44,6 +44,8 @@ struct RaynContext {
   size_t cap_planes = 0;
   int* d_pack_ids = nullptr;
   size_t cap_pack_ids = 0;
+  unsigned char* d_post = nullptr;
+  size_t cap_post = 0;
   RaynStats stats;
   bool qlog_enabled = false;
   std::vector<int32_t> qlog;
@@ -218,6 +220,7 @@ void rayn_b200_destroy(RaynContext* ctx) {
   cudaFree(ctx->pb.counters);
   cudaFree(ctx->d_work_ctr);
   cudaFree(ctx->d_pack_ids);
+  cudaFree(ctx->d_post);
   cudaFree(ctx->d_s1), cudaFree(ctx->d_s2), cudaFree(ctx->d_scr), cudaFree(ctx->d_fis), cudaFree(ctx->d_planes);
   for (auto& t : ctx->timed) cudaEventDestroy(t.a), cudaEventDestroy(t.b);
   cudaEventDestroy(ctx->ev0), cudaEventDestroy(ctx->ev1);
@@ -553,6 +556,41 @@ int32_t rayn_b200_film_pack_tiles(RaynContext* ctx, int32_t W, int32_t H, int32_
 int32_t rayn_b200_film_unpack_tiles(RaynContext* ctx, int32_t W, int32_t H, int32_t tw, int32_t th, const int32_t* tile_list, int32_t n_tiles,
                                     const float* slab_dev, const RaynFilmPlanes* planes_dev) {
   return pack_unpack(ctx, W, H, tw, th, tile_list, n_tiles, planes_dev, const_cast<float*>(slab_dev), 1);
+}
+
+// ---- film post-process (film.rs:205-377 arithmetic) -------------------------------------------------
+int32_t rayn_b200_film_postprocess(RaynContext* ctx, int32_t mode, int32_t W, int32_t H, const RaynFilmPlanes* pl, uint8_t* out,
+                                   int32_t out_space) {
+  if (!ctx) return fail(nullptr, RAYN_ERR_INVALID_ARG, "ctx is NULL");
+  if (mode < 0 || mode > RAYN_POST_ALPHA || W <= 0 || H <= 0 || !pl || !out) return fail(ctx, RAYN_ERR_INVALID_ARG, "film_postprocess: bad argument");
+  const bool need_color = mode <= RAYN_POST_COLOR_ONLY, need_bg = mode == RAYN_POST_COLOR_PLUS_BACKGROUND || mode == RAYN_POST_BACKGROUND;
+  const bool need_alpha = mode == RAYN_POST_COLOR_ALPHA || mode == RAYN_POST_ALPHA, need_normal = mode == RAYN_POST_WORLD_NORMAL;
+  if ((need_color && !pl->color) || (need_bg && !pl->background) || (need_alpha && !pl->alpha) || (need_normal && !pl->normal))
+    return fail(ctx, RAYN_ERR_INVALID_ARG, "Attempted to write a channel with insufficient channels");  // film.rs:294-298
+  CU(cudaSetDevice(ctx->device));
+  const size_t npx = (size_t)W * H, nbytes = npx * post_bytes_per_pixel(mode);
+  cudaStream_t st = ctx->stream;
+  const float *c = pl->color, *a = pl->alpha, *b = pl->background, *n = pl->normal;
+  CU(cudaDeviceSynchronize());
+  if (pl->space == RAYN_MEM_HOST) {
+    CU(regrow(&ctx->d_planes, &ctx->cap_planes, npx * 10));
+    float* d = ctx->d_planes;
+    if (need_color) CU(cudaMemcpyAsync(d, pl->color, npx * 12, cudaMemcpyHostToDevice, st));
+    if (need_alpha) CU(cudaMemcpyAsync(d + 3 * npx, pl->alpha, npx * 4, cudaMemcpyHostToDevice, st));
+    if (need_bg) CU(cudaMemcpyAsync(d + 4 * npx, pl->background, npx * 12, cudaMemcpyHostToDevice, st));
+    if (need_normal) CU(cudaMemcpyAsync(d + 7 * npx, pl->normal, npx * 12, cudaMemcpyHostToDevice, st));
+    c = d, a = d + 3 * npx, b = d + 4 * npx, n = d + 7 * npx;
+  }
+  unsigned char* dout = out;
+  if (out_space == RAYN_MEM_HOST) {
+    CU(regrow(&ctx->d_post, &ctx->cap_post, nbytes));
+    dout = ctx->d_post;
+  }
+  k_postprocess<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(mode, W, H, c, a, b, n, dout);
+  CU(cudaGetLastError());
+  if (out_space == RAYN_MEM_HOST) CU(cudaMemcpyAsync(out, dout, nbytes, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return RAYN_OK;
 }
 
 // ---- known-answer entry points ----------------------------------------------------------------------

@@ -1629,6 +1629,61 @@ __global__ void k_film_pack(int W, int H, int tile_w, int tile_h, int nty, const
 }
 
 // ------------------------------------------------------------------------------------------
+// Film post-process: the per-pixel arithmetic of Film::save_to, film.rs:205-377.
+// One thread per output pixel; a streaming kernel (<= 28 B in, <= 4 B out per pixel).
+// ------------------------------------------------------------------------------------------
+// f32 scalar semantics of the reference: `x.max(0.0).min(1.0)` and `(v*255.0).min(255.0).max(0.0) as u8`
+// use Rust's f32::min/max (NaN loses) and a saturating, truncating cast.
+__host__ __device__ inline float post_saturate(float x) {
+  float a = (x != x) ? 0.0f : (x > 0.0f ? x : 0.0f);
+  return a < 1.0f ? a : 1.0f;
+}
+__host__ __device__ inline float post_gamma(float x) { return dm::pow(x, 1.0f / 2.2f); }  // spectrum.rs:30-32
+__host__ __device__ inline unsigned char post_u8(float v) {
+  float a = v * 255.0f;
+  a = (a != a) ? 255.0f : (a < 255.0f ? a : 255.0f);
+  a = a > 0.0f ? a : 0.0f;
+  return (unsigned char)(int)a;
+}
+__host__ __device__ inline int post_bytes_per_pixel(int mode) { return mode == RAYN_POST_COLOR_ALPHA ? 4 : (mode == RAYN_POST_ALPHA ? 1 : 3); }
+__host__ __device__ inline void post_pixel(int mode, const float* __restrict__ color, const float* __restrict__ alpha,
+                                           const float* __restrict__ background, const float* __restrict__ normal, size_t src,
+                                           unsigned char* dst) {
+  switch (mode) {
+    case RAYN_POST_COLOR_PLUS_BACKGROUND:
+      for (int c = 0; c < 3; ++c) dst[c] = post_u8(post_gamma(post_saturate(color[3 * src + c] + background[3 * src + c])));
+      break;
+    case RAYN_POST_COLOR_ALPHA:
+      for (int c = 0; c < 3; ++c) dst[c] = post_u8(post_gamma(post_saturate(color[3 * src + c])));
+      dst[3] = post_u8(alpha[src]);
+      break;
+    case RAYN_POST_COLOR_ONLY:
+      for (int c = 0; c < 3; ++c) dst[c] = post_u8(post_gamma(color[3 * src + c]));
+      break;
+    case RAYN_POST_BACKGROUND:
+      for (int c = 0; c < 3; ++c) dst[c] = post_u8(post_gamma(post_saturate(background[3 * src + c])));
+      break;
+    case RAYN_POST_WORLD_NORMAL:
+      for (int c = 0; c < 3; ++c) dst[c] = post_u8(normal[3 * src + c] * 0.5f + 0.5f);
+      break;
+    default:
+      dst[0] = post_u8(alpha[src]);
+  }
+}
+__global__ void __launch_bounds__(256) k_postprocess(int mode, int W, int H, const float* __restrict__ color, const float* __restrict__ alpha,
+                                                     const float* __restrict__ background, const float* __restrict__ normal,
+                                                     unsigned char* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)W * H) return;
+  const int x = (int)(i % W), y = (int)(i / W);
+  const size_t src = (size_t)x + (size_t)(H - 1 - y) * W;  // film.rs:236
+  unsigned char px[4];
+  post_pixel(mode, color, alpha, background, normal, src, px);
+  const int bpp = post_bytes_per_pixel(mode);
+  for (int c = 0; c < bpp; ++c) out[(size_t)i * bpp + c] = px[c];
+}
+
+// ------------------------------------------------------------------------------------------
 // known-answer kernels (tests only)
 // ------------------------------------------------------------------------------------------
 __global__ void k_kat_detmath(int op, long long n, const float* a, const float* b, float* out) {

@@ -128,6 +128,15 @@ class Renderer:
         self.render(f, p)
         return planes
 
+    def postprocess(self, mode, width, height, planes):
+        """Film::save_to pixel arithmetic on the device (film.rs:205-377): numpy planes in, uint8 [H, W, bpp] out (rows top to bottom)."""
+        def ptr(k):
+            return planes[k].ctypes.data if planes.get(k) is not None else None
+        p = L.RaynFilmPlanes(ptr("color"), ptr("alpha"), ptr("background"), ptr("normal"), L.MEM_HOST)
+        out = np.zeros((height, width, L.POST_BYTES[mode]), np.uint8)
+        L.check(self._lib.rayn_b200_film_postprocess(self._ctx, mode, width, height, C.byref(p), out.ctypes.data, L.MEM_HOST), self._ctx)
+        return out
+
     # ---- known-answer entry points (tests) ----
     def kat_detmath(self, op, a, b=None):
         a = np.ascontiguousarray(a, np.float32)
@@ -206,6 +215,37 @@ class Film:
         for k in self.channel_kinds:
             self.channels[k] = planes[k].reshape((h, w, 3) if k != "alpha" else (h, w))
         self.progressive_epoch += 1  # film.rs:657
+
+    def save_to(self, write_channels, output_folder, base_name, transparent_background=False):
+        """film.rs:205-377.  Same channel semantics and file names as the reference; the pixel arithmetic runs on the
+        device (`rayn_b200_film_postprocess`), the PNG encoding stays host I/O (PIL)."""
+        import os
+        from PIL import Image
+        os.makedirs(output_folder, exist_ok=True)
+        w, h = self.res
+        flat = {k: np.ascontiguousarray(v, np.float32).reshape(-1) for k, v in self.channels.items()}
+        written = []
+        for kind in write_channels:
+            if kind == "color":
+                if transparent_background and "color" in flat and "alpha" in flat:
+                    mode, pil = L.POST_COLOR_ALPHA, "RGBA"
+                elif not transparent_background and "color" in flat and "background" in flat:
+                    mode, pil = L.POST_COLOR_PLUS_BACKGROUND, "RGB"
+                elif not transparent_background and "color" in flat:
+                    mode, pil = L.POST_COLOR_ONLY, "RGB"
+                else:
+                    raise ValueError("Attempted to write Color channel with insufficient channels")  # film.rs:294-298
+            elif kind in ("background", "normal", "alpha"):
+                if kind not in flat:
+                    raise ValueError(f"Attempted to write {kind} channel but it didn't exist")
+                mode, pil = {"background": (L.POST_BACKGROUND, "RGB"), "normal": (L.POST_WORLD_NORMAL, "RGB"), "alpha": (L.POST_ALPHA, "L")}[kind]
+            else:
+                raise ValueError(kind)
+            px = self._renderer.postprocess(mode, w, h, flat)
+            path = os.path.join(output_folder, f"{base_name}_{kind}.png")
+            Image.fromarray(px[:, :, 0] if pil == "L" else px, pil).save(path)
+            written.append(path)
+        return written
 
     def tonemapped_rgb8(self):
         """The display formula of save_to (film.rs:253-267): (color + background).saturated().gamma(2.2), y flipped."""

@@ -162,3 +162,26 @@ def test_oracle_reproduces_committed_golden(oracle, name):
     g = np.load(os.path.join(GOLD, name + ".npz"))
     for ch in CH:
         assert_bit_equal(o[ch], g[ch], f"{name} {ch}")
+
+
+def test_film_postprocess_formulas(oracle):
+    """save_to pixel arithmetic (film.rs:205-377) against an independent numpy statement (1 LSB slack for pow)."""
+    rng = np.random.default_rng(0)
+    w, h = 13, 9
+    pl = {"color": rng.uniform(-0.2, 1.5, 3 * w * h).astype(np.float32), "alpha": rng.uniform(-0.1, 1.1, w * h).astype(np.float32),
+          "background": rng.uniform(0, 0.5, 3 * w * h).astype(np.float32), "normal": rng.uniform(-1, 1, 3 * w * h).astype(np.float32)}
+    col, bg = pl["color"].reshape(h, w, 3).astype(np.float64), pl["background"].reshape(h, w, 3).astype(np.float64)
+    g = lambda x: np.clip(x, 0, 1) ** (1 / 2.2) * 255
+    want = {L.POST_COLOR_PLUS_BACKGROUND: g(col + bg), L.POST_COLOR_ALPHA: g(col), L.POST_BACKGROUND: g(bg),
+            L.POST_WORLD_NORMAL: np.clip((pl["normal"].reshape(h, w, 3) * 0.5 + 0.5) * 255, 0, 255),
+            L.POST_ALPHA: np.clip(pl["alpha"].reshape(h, w, 1) * 255, 0, 255)}
+    for mode, ref in want.items():
+        got = oracle.film_postprocess(mode, w, h, pl).astype(int)
+        assert got.shape[:2] == (h, w)
+        assert np.abs(got[..., :ref.shape[2]] - np.floor(ref[::-1]).astype(int)).max() <= 1, mode  # y flipped, film.rs:236
+    rgba = oracle.film_postprocess(L.POST_COLOR_ALPHA, w, h, pl)
+    assert np.array_equal(rgba[..., 3:], oracle.film_postprocess(L.POST_ALPHA, w, h, pl))
+    # COLOR_ONLY does not saturate (film.rs:275-293): values > 1 clip at 255, negatives become NaN.powf -> 255 after .min(255)
+    only = oracle.film_postprocess(L.POST_COLOR_ONLY, w, h, pl)
+    neg = (pl["color"].reshape(h, w, 3)[::-1] < 0)
+    assert (only[neg] == 255).all()

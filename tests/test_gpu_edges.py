@@ -128,3 +128,30 @@ def test_limits_are_reported_not_crashed():
         assert e.value.code == L.RAYN_ERR_UNSUPPORTED
     finally:
         r.close()
+
+
+def test_film_postprocess_bit_exact_and_save_to(renderer, oracle, tmp_path):
+    """SURVEY §8f rank 3: Film::save_to's pixel arithmetic on the device vs the oracle (u8 exact), then the
+    Python Film.save_to writes the reference's file set."""
+    rng = np.random.default_rng(5)
+    w, h = 97, 41
+    pl = {"color": rng.uniform(-0.2, 1.5, 3 * w * h).astype(np.float32), "alpha": rng.uniform(-0.1, 1.1, w * h).astype(np.float32),
+          "background": rng.uniform(0, 0.5, 3 * w * h).astype(np.float32), "normal": rng.uniform(-1, 1, 3 * w * h).astype(np.float32)}
+    pl["color"][:6] = [np.nan, np.inf, -np.inf, 0.0, 1.0, 1e-30]
+    pl["alpha"][:3] = [np.nan, 2.0, -1.0]
+    for mode in range(6):
+        g = renderer.postprocess(mode, w, h, pl)
+        o = oracle.film_postprocess(mode, w, h, pl)
+        assert np.array_equal(g, o), f"post-process mode {mode}"
+    from PIL import Image
+    from rayn_b200 import BlackmanHarrisFilter, Film
+    c = configs.baseline_config(3, res=(48, 32), samples=1, max_bounces=2)
+    film = Film(["color", "alpha", "background", "normal"], (48, 32))
+    film.render_frame_into(c["world"], c["camera"], c["integrator"], BlackmanHarrisFilter(1.5), (16, 16), 1, TR, 1)
+    files = film.save_to(["alpha", "normal", "color"], str(tmp_path), "4_spp", False)  # main.rs:86-96
+    assert [f.split("/")[-1] for f in files] == ["4_spp_alpha.png", "4_spp_normal.png", "4_spp_color.png"]
+    img = np.asarray(Image.open(files[2]))
+    flat = {k: np.ascontiguousarray(v, np.float32).reshape(-1) for k, v in film.channels.items()}
+    assert np.array_equal(img, oracle.film_postprocess(L.POST_COLOR_PLUS_BACKGROUND, 48, 32, flat))
+    with pytest.raises(ValueError):
+        Film(["alpha"], (16, 16)).save_to(["color"], str(tmp_path), "x")
