@@ -288,6 +288,11 @@ int32_t rayn_b200_host_rd_tables(int32_t spp, int32_t sets_1d, int32_t sets_2d, 
                                  float* out_1d, float* out_2d);
 int32_t rayn_b200_host_scramble(int32_t width, int32_t height, float* out);
 int32_t rayn_b200_host_fis_blackman_harris(float radius, float* out512);
+/* the same tables / scramble plane generated directly in device memory (DEVICE pointers; bit-identical
+ * to the host builders) - saves uploading W*H floats of scramble per frame (133 MB at 8K)           */
+int32_t rayn_b200_device_frame_inputs(RaynContext* ctx, int32_t width, int32_t height, int32_t spp, int32_t sets_1d,
+                                      int32_t sets_2d, uint64_t offset, float* out_1d_dev, float* out_2d_dev,
+                                      float* scramble_dev);
 /* tile count per film.rs:399-404 (including its partial-tile quirk) */
 int32_t rayn_b200_host_tile_grid(int32_t width, int32_t height, int32_t tile_w, int32_t tile_h,
                                  int32_t* n_tiles_x, int32_t* n_tiles_y);

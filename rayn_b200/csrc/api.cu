@@ -593,6 +593,21 @@ int32_t rayn_b200_film_postprocess(RaynContext* ctx, int32_t mode, int32_t W, in
   return RAYN_OK;
 }
 
+int32_t rayn_b200_device_frame_inputs(RaynContext* ctx, int32_t W, int32_t H, int32_t spp, int32_t sets_1d, int32_t sets_2d, uint64_t offset,
+                                      float* s1, float* s2, float* scramble) {
+  if (!ctx) return fail(nullptr, RAYN_ERR_INVALID_ARG, "ctx is NULL");
+  if (spp <= 0 || sets_1d < 0 || sets_2d < 0 || (sets_1d && !s1) || (sets_2d && !s2) || (scramble && (W <= 0 || H <= 0)))
+    return fail(ctx, RAYN_ERR_INVALID_ARG, "device_frame_inputs: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaDeviceSynchronize());
+  const long long n = (long long)spp * (sets_1d + sets_2d);
+  if (n > 0) k_gen_rd_tables<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(spp, sets_1d, sets_2d, offset, s1, s2);
+  if (scramble) k_gen_scramble<<<(unsigned)(((long long)W * H + 255) / 256), 256, 0, ctx->stream>>>(W, H, scramble);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));
+  return RAYN_OK;
+}
+
 // ---- known-answer entry points ----------------------------------------------------------------------
 #define KAT_PROLOGUE                                                     \
   if (!ctx) return fail(nullptr, RAYN_ERR_INVALID_ARG, "ctx is NULL");   \

@@ -487,11 +487,11 @@ __global__ void __launch_bounds__(EXT_T, 6) k_extend2(const __grid_constant__ De
   warp_add(pb.counters + CNT_EVALS_EXTEND, evals);
 }
 
-// ---- K2 v3: persistent closest-hit kernel.  v2 still idles lanes at the tail of every 2048-ray
-// chunk (ncu r1v2: 19 of 32 lanes at the distance-eval site).  v3 flattens the per-tile live
-// lists into 128-ray batches numbered across the whole pass (k_scan_live builds the prefix),
-// and resident warps pull batches from ONE global counter until the pass is drained: the only
-// tail left is at the very end of the kernel.
+// ---- pass-wide work distribution for the persistent march kernels.  v2 still idles lanes at the
+// tail of every 2048-ray chunk (ncu r1v2: 19 of 32 lanes at the distance-eval site), so the
+// per-tile live lists are flattened into 128-ray batches numbered across the whole pass
+// (k_scan_live builds the prefix) and resident warps pull batches from ONE global counter until
+// the pass is drained: the only tail left is at the very end of the kernel.
 #define EXT_BATCH 128
 #define SCAN_T 1024
 __global__ void __launch_bounds__(SCAN_T) k_scan_live(const PassBufs pb, int* __restrict__ batch_prefix, int* __restrict__ work_ctr) {
@@ -532,116 +532,6 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_live(const PassBufs pb, int* __
     __syncthreads();
   }
   if (tid == 0) batch_prefix[pb.n_tiles] = carry;
-}
-
-__global__ void __launch_bounds__(EXT_T, 6) k_extend3(const __grid_constant__ DevScene sc, const PassBufs pb, const Thr thr,
-                                                      const int* __restrict__ batch_prefix, int* __restrict__ work_ctr) {
-  __shared__ RaynHitable s_hit[RAYN_MAX_HITABLES];
-  for (int k = threadIdx.x; k < sc.n_hit; k += EXT_T) s_hit[k] = sc.hit[k];
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const unsigned lt = (1u << lane) - 1u;
-  const int n_hit = sc.n_hit;
-  const float S = sc.rc.sdf_detail_scale;
-  const float c0 = 0.00005f * S, c1 = 0.05f * S;
-  const int max_marches = sc.rc.max_marches;
-  const float t_max0 = sc.rc.world_radius * 2.0f;
-  const int n_batches = batch_prefix[pb.n_tiles];
-
-  bool have = false, marching = false, exhausted = false;
-  f3 o = {0, 0, 0}, d = {0, 0, 0};
-  float closest = 0.0f, t = 0.0f;
-  int id = -1, hidx = 0, steps = 0, evals = 0, rays = 0;
-  size_t q = 0, g = 0;
-  int cur_ts = 0, cur_pos = 0, cur_end = 0;  // warp-uniform: the batch this warp is draining
-  while (true) {
-    __syncwarp();
-    unsigned idle = __ballot_sync(0xffffffffu, !have);
-    while (idle && !(exhausted && cur_pos >= cur_end)) {
-      if (cur_pos >= cur_end) {  // pull the next batch of the pass
-        int b = 0;
-        if (lane == 0) b = atomicAdd(work_ctr, 1);
-        b = __shfl_sync(0xffffffffu, b, 0);
-        if (b >= n_batches) {
-          exhausted = true;
-          break;
-        }
-        int lo = 0, hi = pb.n_tiles;  // largest ts with batch_prefix[ts] <= b
-        while (hi - lo > 1) {
-          const int mid = (lo + hi) >> 1;
-          if (__ldg(batch_prefix + mid) <= b) lo = mid; else hi = mid;
-        }
-        cur_ts = lo;
-        cur_pos = (b - __ldg(batch_prefix + lo)) * EXT_BATCH;
-        cur_end = min(cur_pos + EXT_BATCH, pb.n_live[lo]);
-      }
-      const int avail = cur_end - cur_pos;
-      const int rank = __popc(idle & lt);
-      if (!have && rank < avail) {
-        q = (size_t)cur_ts * pb.R + cur_pos + rank;
-        g = (size_t)cur_ts * pb.R + pb.q_live[q];
-        const float4 o4 = pb.o_time[g], d4 = pb.d_t[g];
-        o = mk3(o4.x, o4.y, o4.z);
-        d = mk3(d4.x, d4.y, d4.z);
-        closest = t_max0;
-        id = -1;
-        hidx = 0;
-        marching = false;
-        have = true;
-        ++rays;
-      }
-      cur_pos += min(avail, __popc(idle));
-      idle = __ballot_sync(0xffffffffu, !have);
-    }
-    if (!__any_sync(0xffffffffu, have)) break;
-    if (have && !marching) {
-      while (hidx < n_hit && s_hit[hidx].kind == RAYN_HITABLE_SPHERE) {
-        const float ts_ = sphere_hit(s_hit[hidx], o, d, closest);
-        if (ts_ < closest) {
-          closest = ts_;
-          id = hidx;
-        }
-        ++hidx;
-      }
-      if (hidx >= n_hit) {
-        pb.d_t[g].w = closest;
-        pb.q_key[q] = id;
-        have = false;
-      }
-    }
-    if (have) {
-      const f3 p = marching ? fma3s(d, t, o) : o;
-      const float dd = sdf_dist(s_hit[hidx], p);
-      ++evals;
-      bool end = false;
-      if (!marching) {
-        t = dd;
-        steps = 0;
-        marching = true;
-        end = t != t;
-      } else {
-        const bool hit = dm::abs(dd) < dm::max(c0, c1 * thr.at(t));
-        const bool gt = t > closest;
-        if (hit || gt) {
-          end = true;
-        } else {
-          t = t + dd;
-          ++steps;
-          end = (t != t) || steps >= max_marches;
-        }
-      }
-      if (end) {
-        if (t < closest) {
-          closest = t;
-          id = hidx;
-        }
-        marching = false;
-        ++hidx;
-      }
-    }
-  }
-  warp_add(pb.counters + CNT_EXTEND_RAYS, rays);
-  warp_add(pb.counters + CNT_EVALS_EXTEND, evals);
 }
 
 // ---- K2 v4: closest hit split by hitable kind.  ncu on k_extend3 (profiles/r01 notes): the
@@ -1681,6 +1571,51 @@ __global__ void __launch_bounds__(256) k_postprocess(int mode, int W, int H, con
   post_pixel(mode, color, alpha, background, normal, src, px);
   const int bpp = post_bytes_per_pixel(mode);
   for (int c = 0; c < bpp; ++c) out[(size_t)i * bpp + c] = px[c];
+}
+
+// ------------------------------------------------------------------------------------------
+// Device-side sampler state: the same R_d tables and SmallRng scramble as
+// host_inputs.cpp, generated in HBM so an 8K frame does not upload a 133 MB scramble plane.
+// Integer arithmetic only -> bit-identical to the host builders (tests compare them).
+// ------------------------------------------------------------------------------------------
+RT_D float dev_rd_value(unsigned long long alpha, unsigned long long n) {
+  const unsigned long long frac = alpha * n + 0x8000000000000000ull;
+  return (float)(frac >> 40) * (1.0f / 16777216.0f);
+}
+__global__ void __launch_bounds__(256) k_gen_rd_tables(int spp, int sets_1d, int sets_2d, unsigned long long offset, float* __restrict__ s1,
+                                                       float* __restrict__ s2) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n1 = (long long)spp * sets_1d, n2 = (long long)spp * sets_2d;
+  if (i < n1) {
+    const int set = (int)(i / spp), n = (int)(i % spp);
+    s1[i] = dev_rd_value(0x9e3779b97f4a7c15ull, ((offset + (unsigned long long)set) << 32) + (unsigned long long)n + 1ull);
+  } else if (i < n1 + n2) {
+    const long long j = i - n1;
+    const int set = (int)(j / spp), n = (int)(j % spp);
+    const unsigned long long base = ((offset + (unsigned long long)sets_1d + (unsigned long long)set) << 32) + (unsigned long long)n + 1ull;
+    s2[2 * j + 0] = dev_rd_value(0xc13fa9a902a6328full, base);
+    s2[2 * j + 1] = dev_rd_value(0x91e10da5c79e7b1cull, base);
+  }
+}
+__global__ void __launch_bounds__(256) k_gen_scramble(int W, int H, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)W * H) return;
+  // rand_core 0.5.1 seed_from_u64 (PCG32 expansion) -> rand_pcg 0.2.1 Mcg128Xsl64 -> first f32 (film.rs:460-461)
+  unsigned long long state = (unsigned long long)i;  // x + y*width
+  unsigned int sd[4];
+  for (int c = 0; c < 4; ++c) {
+    state = state * 6364136223846793005ull + 11634580027462260723ull;
+    const unsigned int xorshifted = (unsigned int)(((state >> 18) ^ state) >> 27);
+    const unsigned int rot = (unsigned int)(state >> 59);
+    sd[c] = (xorshifted >> rot) | (xorshifted << ((32 - rot) & 31));
+  }
+  unsigned __int128 s = ((unsigned __int128)(((unsigned long long)sd[3] << 32) | sd[2]) << 64) | (((unsigned long long)sd[1] << 32) | sd[0]);
+  s |= 1;
+  s = s * (((unsigned __int128)2549297995355413924ull << 64) | 4865540595714422341ull);
+  const unsigned int r2 = (unsigned int)(s >> 122);
+  const unsigned long long xsl = (unsigned long long)(s >> 64) ^ (unsigned long long)s;
+  const unsigned long long o = (xsl >> r2) | (xsl << ((64 - r2) & 63));
+  out[i] = (float)(((unsigned int)o) >> 8) * (1.0f / 16777216.0f);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -155,3 +155,19 @@ def test_film_postprocess_bit_exact_and_save_to(renderer, oracle, tmp_path):
     assert np.array_equal(img, oracle.film_postprocess(L.POST_COLOR_PLUS_BACKGROUND, 48, 32, flat))
     with pytest.raises(ValueError):
         Film(["alpha"], (16, 16)).save_to(["color"], str(tmp_path), "x")
+
+
+def test_device_side_frame_inputs_equal_host_builders(renderer):
+    """R_d tables and the SmallRng scramble plane generated in HBM are bit-identical to the host builders."""
+    import torch
+    integ = PathTracingIntegrator(3, 2)
+    inp = FrameInputs(301, 77, 5, integ, frame=7)
+    dev = torch.device("cuda", 0)
+    s1 = torch.empty(inp.samples_1d.size, dtype=torch.float32, device=dev)
+    s2 = torch.empty(inp.samples_2d.size, dtype=torch.float32, device=dev)
+    sc = torch.empty(inp.scramble.size, dtype=torch.float32, device=dev)
+    L.check(L.lib().rayn_b200_device_frame_inputs(renderer.ctx, 301, 77, inp.spp, inp.sets_1d, inp.sets_2d, 7, s1.data_ptr(), s2.data_ptr(),
+                                                  sc.data_ptr()), renderer.ctx)
+    assert_bit_equal(s1.cpu().numpy(), inp.samples_1d, "1-D tables")
+    assert_bit_equal(s2.cpu().numpy(), inp.samples_2d, "2-D tables")
+    assert_bit_equal(sc.cpu().numpy(), inp.scramble, "scramble")
