@@ -331,13 +331,16 @@ RT_D void shading_info(const DevScene& sc, const RaynHitable& h, Thr thr, Shadin
     sp.offset_by = 0.0f;
   } else {
     float eps = dm::max(0.0001f, sc.rc.sdf_detail_scale * thr.at(sp.t));
-    f3 xyy = {1.0f, -1.0f, -1.0f}, yyx = {-1.0f, -1.0f, 1.0f}, yxy = {-1.0f, 1.0f, -1.0f}, xxx = {1.0f, 1.0f, 1.0f};
-    float d0 = sdf_dist(h, sp.point + xyy * eps);
-    float d1 = sdf_dist(h, sp.point + yyx * eps);
-    float d2 = sdf_dist(h, sp.point + yxy * eps);
-    float d3 = sdf_dist(h, sp.point + xxx * eps);
+    // tetrahedron offsets xyy, yyx, yxy, xxx in that order; rolled loop (one inlined copy of the distance
+    // estimator instead of four: the kernel was stalling on instruction fetch), same left-to-right sum
+    f3 n = {0.0f, 0.0f, 0.0f};
+#pragma unroll 1
+    for (int i = 0; i < 4; ++i) {
+      const f3 k = {(i == 0 || i == 3) ? 1.0f : -1.0f, (i == 2 || i == 3) ? 1.0f : -1.0f, (i == 1 || i == 3) ? 1.0f : -1.0f};
+      const float d = sdf_dist(h, sp.point + k * eps);
+      n = i == 0 ? k * d : n + k * d;
+    }
     *evals += 4;
-    f3 n = xyy * d0 + yyx * d1 + yxy * d2 + xxx * d3;
     sp.normal = normalized(n);
     sp.offset_by = eps;
   }
