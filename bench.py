@@ -305,6 +305,15 @@ def main():
     if not fused_shade:
         per_kernel["shade_pre"]["lanes"] = int(ts.shade_lanes)
         per_kernel["shade_pre"]["hbm_gbs_algorithmic"] = ts.shade_lanes * ALG_BYTES_SHADE / max(shade_s, 1e-12) / 1e9
+    # the genuinely HBM-bound streaming kernels, for context next to the issue-bound march kernels
+    ALG_BYTES_RAYGEN = 88.0   # writes o_time, d_t, rad, thr, nrm0 (5 x float4) + term + q_live per path
+    ALG_BYTES_RESOLVE = 36.0  # reads rad + nrm0 (2 x float4) + term per path (+ 40 B per pixel out)
+    if "raygen" in per_kernel:
+        per_kernel["raygen"]["hbm_gbs_algorithmic"] = ts.paths * ALG_BYTES_RAYGEN / max(kms["raygen"] * 1e-3, 1e-12) / 1e9
+        per_kernel["raygen"]["hbm_frac"] = per_kernel["raygen"]["hbm_gbs_algorithmic"] / hbm_peak
+    if "resolve" in per_kernel:
+        per_kernel["resolve"]["hbm_gbs_algorithmic"] = (ts.paths * ALG_BYTES_RESOLVE + w * h * 40.0) / max(kms["resolve"] * 1e-3, 1e-12) / 1e9
+        per_kernel["resolve"]["hbm_frac"] = per_kernel["resolve"]["hbm_gbs_algorithmic"] / hbm_peak
     dom = max(kms, key=kms.get) if kms else "extend"
     dom_name = {"extend": "k_extend_march (closest-hit sphere-march)", "shadow": "k_shadow (occlusion sphere-march)",
                 "shade_pre": "k_shade_pre", "shade_post": "k_shade_post"}.get(dom, dom)

@@ -1045,7 +1045,7 @@ RT_D SlotCtx slot_ctx(const DevScene& sc, const DevFrame& fr, const PassBufs& pb
   return c;
 }
 
-__global__ void __launch_bounds__(128, 6) k_shade_pre(const __grid_constant__ DevScene sc, const DevFrame fr, const PassBufs pb,
+__global__ void __launch_bounds__(128, 8) k_shade_pre(const __grid_constant__ DevScene sc, const DevFrame fr, const PassBufs pb,
                                                       const int depth, const Thr thr) {
   const int ts = blockIdx.y;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1225,7 +1225,7 @@ __global__ void __launch_bounds__(SHD_T, 8) k_shadow(const __grid_constant__ Dev
   warp_add(pb.counters + CNT_EVALS_SHADOW, evals);
 }
 
-__global__ void __launch_bounds__(128, 6) k_shade_post(const __grid_constant__ DevScene sc, const DevFrame fr, const PassBufs pb,
+__global__ void __launch_bounds__(128, 8) k_shade_post(const __grid_constant__ DevScene sc, const DevFrame fr, const PassBufs pb,
                                                        const int depth) {
   const int ts = blockIdx.y;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
