@@ -192,7 +192,7 @@ int32_t rayn_b200_create(const RaynConfig* cfg, RaynContext** out_ctx) {
   ctx = new RaynContext();
   ctx->device = dev;
   ctx->flags = cfg ? cfg->flags : 0;
-  ctx->cap_paths = (cfg && cfg->max_paths_per_pass > 0) ? cfg->max_paths_per_pass : (int64_t)48 << 20;
+  ctx->cap_paths = (cfg && cfg->max_paths_per_pass > 0) ? cfg->max_paths_per_pass : (int64_t)96 << 20;  // ~25 GB of path state + shadow queue; fewer passes = fewer kernel tails (measured +3.5 %)
   memset(&ctx->pb, 0, sizeof ctx->pb);
   memset(&ctx->stats, 0, sizeof ctx->stats);
   memset(&ctx->scene, 0, sizeof ctx->scene);
