@@ -73,6 +73,11 @@ typedef struct RaynHitable {
   /* Mandelbulb (authored): power is fixed to 8 in this build; bailout radius.             */
   int32_t bulb_power;
   float bulb_bailout;
+  /* Sphere<TR> with a time-varying centre: centre(t) = center + center_velocity * t,
+   * i.e. what the closure `|t| center + velocity * t` gives through `impl WSequenced<Wec3> for Fn(f32)->Vec3`
+   * (src/animation.rs:62-67) - which evaluates the closure at LANE 0's time for the whole 4-lane packet.
+   * All-zero velocity = the constant `impl_inherent_wsequenced` path (animation.rs:52).               */
+  float center_velocity[3];
 } RaynHitable;
 
 /* ---- Material / BSDF (src/material.rs:11-38) -------------------------------------- */
@@ -119,6 +124,13 @@ typedef struct RaynCamera {
   float up[3];
   float focus[3];        /* thin lens: focus point                                         */
   float aperture;        /* thin lens                                                      */
+  /* linear-in-time camera parameters, same closure semantics as RaynHitable.center_velocity
+   * (camera.rs:90-92,177-182,258-260 sample origin/at/up/focus/aperture at the packet's time)      */
+  float origin_velocity[3];
+  float at_velocity[3];
+  float up_velocity[3];
+  float focus_velocity[3];
+  float aperture_rate;
 } RaynCamera;
 
 /* ---- VolumeParams (src/volume.rs:2-5): Option<f32> pairs --------------------------- */

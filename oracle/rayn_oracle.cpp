@@ -482,12 +482,22 @@ inline F4 sdf_hit(const RaynHitable& h, const RaynRenderConsts& rc, V3 origin, V
   return t;
 }
 
+// WSequenced<Wec3>::sample_at (animation.rs).  Constants: impl_inherent_wsequenced (:52).  A parameter with a
+// non-zero velocity stands for the closure `|t| base + velocity * t`, whose impl (:62-67) evaluates the closure at
+// LANE 0's time and broadcasts it to all four lanes.
+inline V3 seq_v3(const float* base, const float* vel, F4 time) {
+  if (vel[0] == 0.0f && vel[1] == 0.0f && vel[2] == 0.0f) return v3splat(base[0], base[1], base[2]);
+  const float t0 = time[0];
+  return v3splat(base[0] + vel[0] * t0, base[1] + vel[1] * t0, base[2] + vel[2] * t0);
+}
+inline F4 seq_f(float base, float rate, F4 time) { return rate == 0.0f ? splat(base) : splat(base + rate * time[0]); }
+
 // ---- Sphere (sphere.rs) --------------------------------------------------------------------
-inline F4 sphere_occluded(const RaynHitable& h, V3 start, V3 end) {  // :24-46
+inline F4 sphere_occluded(const RaynHitable& h, V3 start, V3 end, F4 time) {  // :24-46
   V3 dir = end - start;
   F4 dist = mag(dir);
   dir = dir / dist;
-  V3 origin = v3splat(h.center[0], h.center[1], h.center[2]);
+  V3 origin = seq_v3(h.center, h.center_velocity, time);
   V3 oc = start - origin;
   F4 b = dot(oc, dir);
   F4 c = mag_sq(oc) - splat(h.radius * h.radius);
@@ -500,8 +510,8 @@ inline F4 sphere_occluded(const RaynHitable& h, V3 start, V3 end) {  // :24-46
   F4 valid = cmp_gt(mn, splat(0.001f)) & cmp_le(t1, dist) & desc_pos;
   return merge(valid, splat(0.0f), splat(1.0f));
 }
-inline F4 sphere_hit(const RaynHitable& h, V3 ro, V3 rd, F4 t_max) {  // :48-72
-  V3 origin = v3splat(h.center[0], h.center[1], h.center[2]);
+inline F4 sphere_hit(const RaynHitable& h, V3 ro, V3 rd, F4 t_max, F4 time) {  // :48-72
+  V3 origin = seq_v3(h.center, h.center_velocity, time);
   V3 oc = ro - origin;
   F4 b = dot(oc, rd);
   F4 c = mag_sq(oc) - splat(h.radius * h.radius);
@@ -554,25 +564,25 @@ inline ShadingPoint sdf_shading_info(const RaynHitable& h, const RaynRenderConst
 }
 inline ShadingPoint sphere_shading_info(const RaynHitable& h, const WHit& hit) {  // sphere.rs:74-86
   V3 point = point_at(hit.ray, hit.t);
-  V3 origin = v3splat(h.center[0], h.center[1], h.center[2]);
+  V3 origin = seq_v3(h.center, h.center_velocity, hit.ray.time);
   V3 normal = normalized(point - origin);
   return make_sp(hit, point, splat(0.0f), normal);
 }
 
 inline F4 hitable_hit(const World& w, int id, const WRay& ray, F4 t_max, const Thr& thr, int64_t* evals) {
   const RaynHitable& h = w.s->hitables[id];
-  if (h.kind == RAYN_HITABLE_SPHERE) return sphere_hit(h, ray.origin, ray.dir, t_max);
+  if (h.kind == RAYN_HITABLE_SPHERE) return sphere_hit(h, ray.origin, ray.dir, t_max, ray.time);
   return sdf_hit(h, w.s->consts, ray.origin, ray.dir, t_max, thr, evals);
 }
-inline F4 hitable_occluded(const World& w, int id, V3 start, V3 end) {
+inline F4 hitable_occluded(const World& w, int id, V3 start, V3 end, F4 time) {
   const RaynHitable& h = w.s->hitables[id];
-  if (h.kind == RAYN_HITABLE_SPHERE) return sphere_occluded(h, start, end);
+  if (h.kind == RAYN_HITABLE_SPHERE) return sphere_occluded(h, start, end, time);
   return sdf_occluded(h, w.s->consts, start, end);
 }
 // hitable.rs:164-168: product over ALL hitables, no early out
-inline F4 test_occluded(const World& w, V3 start, V3 end) {
+inline F4 test_occluded(const World& w, V3 start, V3 end, F4 time) {
   F4 acc = splat(1.0f);
-  for (int i = 0; i < w.n_hit(); ++i) acc = acc * hitable_occluded(w, i, start, end);
+  for (int i = 0; i < w.n_hit(); ++i) acc = acc * hitable_occluded(w, i, start, end, time);
   return acc;
 }
 
@@ -708,13 +718,13 @@ inline V3 surface_sample_one_light(const World& w, int light_idx, F4 s0, F4 s1, 
   F4 dist = mag(wi);
   wi = wi / dist;
   V3 occlude_point = sp.point + sp.normal * f4signum(dot(sp.normal, wi)) * sp.offset_by;
-  F4 occluded = test_occluded(w, occlude_point, end_point);
+  F4 occluded = test_occluded(w, occlude_point, end_point, sp.ray.time);
   V3 f = bsdf_f(mat, wo, wi, sp.normal) * f4max(dot(sp.normal, wi), splat(0.0f));
   F4 transmission = w.s->volume.has_extinction ? f4exp(splat(-w.s->volume.coeff_extinction) * dist) : splat(1.0f);
   return li * f * transmission * occluded / pdf;
 }
 inline V3 volume_sample_one_light(const World& w, int light_idx, F4 ls0, F4 ls1, F4 volume_sample, V3 ray_o,
-                                  V3 ray_d, F4 max_distance, F4* out_t) {  // :242-281
+                                  V3 ray_d, F4 max_distance, F4 time, F4* out_t) {  // :242-281
   const RaynLight& L = w.s->lights[light_idx];
   F4 vol_dist, vol_pdf;
   light_sample_volume(L, volume_sample, ray_o, ray_d, max_distance, &vol_dist, &vol_pdf);
@@ -724,7 +734,7 @@ inline V3 volume_sample_one_light(const World& w, int light_idx, F4 ls0, F4 ls1,
   light_sample(L, ls0, ls1, sampled_point, &end_point, &li, &light_pdf);
   V3 wi = end_point - sampled_point;
   F4 dist_point_to_light = mag(wi);
-  F4 occluded = test_occluded(w, sampled_point, end_point);
+  F4 occluded = test_occluded(w, sampled_point, end_point, time);
   F4 f = splat(1.0f) / (splat(4.0f) * splat(kPI));
   F4 transmission =
       w.s->volume.has_extinction ? f4exp(splat(-w.s->volume.coeff_extinction) * dist_point_to_light) : splat(1.0f);
@@ -776,7 +786,7 @@ void integrate(const World& w, int max_bounces, int volume_marches, const F4* s1
         int li_idx = light_index(s1d[march + 1][i], nl);
         F4 t;
         V3 li = volume_sample_one_light(w, li_idx, s2d[8 + 8 * march + i * 2], s2d[8 + 8 * march + i * 2 + 1],
-                                        s1d[1], sp.ray.origin, sp.ray.dir, sp.t, &t);
+                                        s1d[1], sp.ray.origin, sp.ray.dir, sp.t, sp.ray.time, &t);
         F4 transmission = vol.has_extinction ? f4exp(splat(-vol.coeff_extinction) * t) : splat(1.0f);
         sp.ray.radiance = sp.ray.radiance + li * sp.ray.throughput * correction * rho_s * transmission;
         cnt.shadow_rays += 4;
@@ -833,9 +843,9 @@ void integrate(const World& w, int max_bounces, int volume_marches, const F4* s1
 // ---- camera.rs -------------------------------------------------------------------------------------
 WRay camera_get_rays(const RaynCamera& c, float scramble, const uint32_t* sample_nums, uint32_t tx, uint32_t ty, F4 u,
                      F4 v, F4 time, F4 ls0, F4 ls1) {
-  V3 origin = v3splat(c.origin[0], c.origin[1], c.origin[2]);
-  V3 at = v3splat(c.at[0], c.at[1], c.at[2]);
-  V3 up = v3splat(c.up[0], c.up[1], c.up[2]);
+  V3 origin = seq_v3(c.origin, c.origin_velocity, time);  // self.origin.sample_at(time), camera.rs:90-92
+  V3 at = seq_v3(c.at, c.at_velocity, time);
+  V3 up = seq_v3(c.up, c.up_velocity, time);
   F4 hx = splat(c.half_size[0]), hy = splat(c.half_size[1]);
   V3 ro, rd;
   if (c.kind == RAYN_CAMERA_PINHOLE) {  // :81-114
@@ -848,9 +858,9 @@ WRay camera_get_rays(const RaynCamera& c, float scramble, const uint32_t* sample
     ro = origin;
     rd = normalized(lower_left + horiz + verti - origin);
   } else if (c.kind == RAYN_CAMERA_THINLENS) {  // :168-208
-    V3 focus = v3splat(c.focus[0], c.focus[1], c.focus[2]);
+    V3 focus = seq_v3(c.focus, c.focus_velocity, time);
     F4 focus_dist = mag(focus - origin);
-    F4 aperture = splat(c.aperture);
+    F4 aperture = seq_f(c.aperture, c.aperture_rate, time);
     V3 bw = normalized(origin - at);
     V3 bu = normalized(cross(up, bw));
     V3 bv = cross(bw, bu);
@@ -1204,7 +1214,7 @@ int32_t rayn_oracle_kat_occluded(const RaynSceneDesc* scene, int64_t n, const fl
                                  float* out) {
   World w{scene};
   for (int64_t i = 0; i < n; i += 4)
-    store_f_packet(out, i, n, test_occluded(w, load_v3_packet(start3, i, n), load_v3_packet(end3, i, n)));
+    store_f_packet(out, i, n, test_occluded(w, load_v3_packet(start3, i, n), load_v3_packet(end3, i, n), splat(0.0f)));
   return RAYN_OK;
 }
 

@@ -42,7 +42,7 @@ fp = C.POINTER(C.c_float)
 class RaynHitable(C.Structure):
     _fields_ = [("kind", i32), ("material", i32), ("center", f32 * 3), ("radius", f32),
                 ("iterations", i32), ("box_l", f32), ("min_rad_sq", f32), ("fixed_rad_sq", f32),
-                ("scale", f32), ("bulb_power", i32), ("bulb_bailout", f32)]
+                ("scale", f32), ("bulb_power", i32), ("bulb_bailout", f32), ("center_velocity", f32 * 3)]
 
 
 class RaynMaterial(C.Structure):
@@ -56,7 +56,9 @@ class RaynLight(C.Structure):
 
 class RaynCamera(C.Structure):
     _fields_ = [("kind", i32), ("half_size", f32 * 2), ("full_size", f32 * 2), ("half_pixel_size", f32),
-                ("origin", f32 * 3), ("at", f32 * 3), ("up", f32 * 3), ("focus", f32 * 3), ("aperture", f32)]
+                ("origin", f32 * 3), ("at", f32 * 3), ("up", f32 * 3), ("focus", f32 * 3), ("aperture", f32),
+                ("origin_velocity", f32 * 3), ("at_velocity", f32 * 3), ("up_velocity", f32 * 3), ("focus_velocity", f32 * 3),
+                ("aperture_rate", f32)]
 
 
 class RaynVolume(C.Structure):

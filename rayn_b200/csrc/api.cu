@@ -378,6 +378,11 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
   const bool simple = (ctx->flags & RAYN_FLAG_SIMPLE_MARCH) != 0;
   const bool block_pool = !simple && (ctx->flags & RAYN_FLAG_BLOCK_POOL) != 0 && n_sdf <= SH_MAX_SDF;
   const bool v3 = !simple && !block_pool;
+  bool motion = false;  // time-varying sphere centres need the packet's lane-0 time: only the default kernel family plumbs it
+  for (int i = 0; i < n_hit; ++i)
+    motion |= ctx->scene.hit[i].kind == RAYN_HITABLE_SPHERE && (ctx->scene.hit[i].center_velocity[0] != 0.0f || ctx->scene.hit[i].center_velocity[1] != 0.0f ||
+                                                                 ctx->scene.hit[i].center_velocity[2] != 0.0f);
+  if (motion && !v3) return fail(ctx, RAYN_ERR_UNSUPPORTED, "time-varying sphere centres are only supported by the default kernel family (no RAYN_FLAG_SIMPLE_MARCH / BLOCK_POOL)");
   const bool no_flat = (ctx->flags & RAYN_FLAG_FLATTEN) == 0;
   bool any_bulb = false;
   for (int i = 0; i < n_hit; ++i) any_bulb |= ctx->scene.hit[i].kind == RAYN_HITABLE_MANDELBULB;
@@ -423,7 +428,7 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
           int e = k;
           while (e < n_hit && ctx->scene.hit[e].kind == RAYN_HITABLE_SPHERE) ++e;
           if (e > k || first_kernel) {
-            k_extend_spheres<<<g_paths, 256, 0, st>>>(ctx->scene, pb, k, e, first_kernel);
+            k_extend_spheres<<<g_paths, 256, 0, st>>>(ctx->scene, pb, k, e, first_kernel, motion ? 1 : 0);
             ctx->stats.launches++;
             first_kernel = 0;
           }

@@ -255,11 +255,24 @@ RT_D float sdf_occluded(const RaynHitable& h, const RaynRenderConsts& rc, f3 sta
 }
 
 // ---- Sphere, sphere.rs ------------------------------------------------------------------------
-RT_D float sphere_occluded(const RaynHitable& h, f3 start, f3 end) {  // :24-46
+// WSequenced<Wec3>::sample_at for the sphere centre.  A non-zero velocity stands for the closure
+// `|t| center + velocity * t`, which the reference evaluates at LANE 0's time of the 4-lane packet
+// (animation.rs:62-67): `time0` is that time.  Zero velocity = constant (animation.rs:52).
+RT_D f3 seq3(const float* base, const float* vel, float time0) {
+  f3 c = ld3(base);
+  const f3 v = ld3(vel);
+  if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) c = c + v * time0;
+  return c;
+}
+RT_D f3 sphere_center(const RaynHitable& h, float time0) { return seq3(h.center, h.center_velocity, time0); }
+RT_D bool sphere_moves(const RaynHitable& h) {
+  return h.kind == RAYN_HITABLE_SPHERE && (h.center_velocity[0] != 0.0f || h.center_velocity[1] != 0.0f || h.center_velocity[2] != 0.0f);
+}
+RT_D float sphere_occluded(const RaynHitable& h, f3 start, f3 end, float time0) {  // :24-46
   f3 dir = end - start;
   float dist = mag(dir);
   dir = dir / dist;
-  f3 oc = start - ld3(h.center);
+  f3 oc = start - sphere_center(h, time0);
   float b = dot(oc, dir);
   float c = mag_sq(oc) - h.radius * h.radius;
   float descrim = b * b - c;
@@ -271,8 +284,8 @@ RT_D float sphere_occluded(const RaynHitable& h, f3 start, f3 end) {  // :24-46
   bool valid = (mn > 0.001f) && (t1 <= dist) && desc_pos;
   return valid ? 0.0f : 1.0f;
 }
-RT_D float sphere_hit(const RaynHitable& h, f3 ro, f3 rd, float t_max) {  // :48-72
-  f3 oc = ro - ld3(h.center);
+RT_D float sphere_hit(const RaynHitable& h, f3 ro, f3 rd, float t_max, float time0) {  // :48-72
+  f3 oc = ro - sphere_center(h, time0);
   float b = dot(oc, rd);
   float c = mag_sq(oc) - h.radius * h.radius;
   float descrim = b * b - c;
@@ -288,12 +301,12 @@ RT_D float sphere_hit(const RaynHitable& h, f3 ro, f3 rd, float t_max) {  // :48
 }
 
 // HitableStore::add_hits fold, hitable.rs:177-198
-RT_D void closest_hit(const DevScene& sc, f3 o, f3 d, Thr thr, float* out_t, int* out_obj, int* evals) {
+RT_D void closest_hit(const DevScene& sc, f3 o, f3 d, Thr thr, float* out_t, int* out_obj, int* evals, float time0 = 0.0f) {
   float closest = sc.rc.world_radius * 2.0f;  // film.rs:556
   int id = -1;
   for (int i = 0; i < sc.n_hit; ++i) {
     const RaynHitable& h = sc.hit[i];
-    float t = h.kind == RAYN_HITABLE_SPHERE ? sphere_hit(h, o, d, closest) : sdf_hit(h, sc.rc, o, d, closest, thr, evals);
+    float t = h.kind == RAYN_HITABLE_SPHERE ? sphere_hit(h, o, d, closest, time0) : sdf_hit(h, sc.rc, o, d, closest, thr, evals);
     if (t < closest) {
       closest = t;
       id = i;
@@ -306,9 +319,9 @@ RT_D void closest_hit(const DevScene& sc, f3 o, f3 d, Thr thr, float* out_t, int
 // HitableStore::test_occluded, hitable.rs:164-168.  The reference multiplies occluded() in
 // {0,1} over ALL hitables; a product of exact 0/1 floats is 0 iff any factor is 0, so the
 // cheap analytic spheres are tested first and the march is skipped once occlusion is known.
-RT_D float test_occluded(const DevScene& sc, f3 start, f3 end, int* evals) {
+RT_D float test_occluded(const DevScene& sc, f3 start, f3 end, int* evals, float time0 = 0.0f) {
   for (int i = 0; i < sc.n_hit; ++i)
-    if (sc.hit[i].kind == RAYN_HITABLE_SPHERE && sphere_occluded(sc.hit[i], start, end) == 0.0f) return 0.0f;
+    if (sc.hit[i].kind == RAYN_HITABLE_SPHERE && sphere_occluded(sc.hit[i], start, end, time0) == 0.0f) return 0.0f;
   for (int i = 0; i < sc.n_hit; ++i)
     if (sc.hit[i].kind != RAYN_HITABLE_SPHERE && sdf_occluded(sc.hit[i], sc.rc, start, end, evals) == 0.0f) return 0.0f;
   return 1.0f;
@@ -324,10 +337,11 @@ struct ShadingPoint {  // hitable.rs:21-28 (per lane)
   m3 basis;
 };
 // sdf.rs:85-101 with sdfu's tetrahedral normals_fast (oracle/README.md A8); sphere.rs:74-86
-RT_D void shading_info(const DevScene& sc, const RaynHitable& h, Thr thr, ShadingPoint& sp, int* evals, bool want_basis = true) {
+RT_D void shading_info(const DevScene& sc, const RaynHitable& h, Thr thr, ShadingPoint& sp, int* evals, bool want_basis = true,
+                       float time0 = 0.0f) {
   sp.point = fma3s(sp.d, sp.t, sp.o);  // WHit::point -> ray.point_at, ray.rs:22-24
   if (h.kind == RAYN_HITABLE_SPHERE) {
-    sp.normal = normalized(sp.point - ld3(h.center));
+    sp.normal = normalized(sp.point - sphere_center(h, time0));
     sp.offset_by = 0.0f;
   } else {
     float eps = dm::max(0.0001f, sc.rc.sdf_detail_scale * thr.at(sp.t));
@@ -461,8 +475,9 @@ RT_D int light_index(float s, int n_lights) {  // integrator.rs:76-77 (+ clamp, 
 }
 
 // ---- camera.rs ---------------------------------------------------------------------------------------
-RT_D void camera_ray(const RaynCamera& c, float u, float v, float ls0, float ls1, f3* ro, f3* rd) {
-  f3 origin = ld3(c.origin), at = ld3(c.at), up = ld3(c.up);
+// time0 = the time of lane 0 of the camera packet (the 4 samples 4k..4k+3 of one pixel), see seq3()
+RT_D void camera_ray(const RaynCamera& c, float u, float v, float ls0, float ls1, float time0, f3* ro, f3* rd) {
+  f3 origin = seq3(c.origin, c.origin_velocity, time0), at = seq3(c.at, c.at_velocity, time0), up = seq3(c.up, c.up_velocity, time0);
   float hx = c.half_size[0], hy = c.half_size[1];
   if (c.kind == RAYN_CAMERA_PINHOLE) {  // :81-114
     f3 bw = normalized(origin - at);
@@ -474,7 +489,8 @@ RT_D void camera_ray(const RaynCamera& c, float u, float v, float ls0, float ls1
     *ro = origin;
     *rd = normalized(lower_left + horiz + verti - origin);
   } else if (c.kind == RAYN_CAMERA_THINLENS) {  // :168-208
-    float focus_dist = mag(ld3(c.focus) - origin);
+    float focus_dist = mag(seq3(c.focus, c.focus_velocity, time0) - origin);
+    const float aperture = c.aperture_rate == 0.0f ? c.aperture : c.aperture + c.aperture_rate * time0;
     f3 bw = normalized(origin - at);
     f3 bu = normalized(cross(up, bw));
     f3 bv = cross(bw, bu);
@@ -483,8 +499,8 @@ RT_D void camera_ray(const RaynCamera& c, float u, float v, float ls0, float ls1
     f3 verti = bv * hy * focus_dist * 2.0f * v;
     float dx, dy;
     concentric(ls0, ls1, &dx, &dy);
-    dx = dx * c.aperture;
-    dy = dy * c.aperture;
+    dx = dx * aperture;
+    dy = dy * aperture;
     f3 offset = bu * dx + bv * dy;
     f3 o2 = origin + offset;
     *ro = o2;

@@ -113,8 +113,9 @@ __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ DevScene
   const float v = (1.0f / (float)fr.H) * sy;
   const float time = fr.t0 + (fr.t1 - fr.t0) * samp1(fr, s, scramble, 0);
   const float ls0 = samp2(fr, 0, s, scramble, 1), ls1 = samp2(fr, 1, s, scramble, 1);
+  const float time0 = fr.t0 + (fr.t1 - fr.t0) * samp1(fr, s & ~3, scramble, 0);  // lane 0 of this sample's camera packet
   f3 ro, rd;
-  camera_ray(sc.cam, u, v, ls0, ls1, &ro, &rd);
+  camera_ray(sc.cam, u, v, ls0, ls1, time0, &ro, &rd);
   const size_t g = (size_t)ts * pb.R + i;
   pb.o_time[g] = make_float4(ro.x, ro.y, ro.z, time);
   pb.d_t[g] = make_float4(rd.x, rd.y, rd.z, 0.0f);
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(EXT_T, 6) k_extend2(const __grid_constant__ De
     if (!__any_sync(0xffffffffu, have)) break;
     if (have && !marching) {  // analytic hitables up to the next SDF (hitable.rs:177-198 fold order)
       while (hidx < n_hit && s_hit[hidx].kind == RAYN_HITABLE_SPHERE) {
-        const float ts_ = sphere_hit(s_hit[hidx], o, d, closest);
+        const float ts_ = sphere_hit(s_hit[hidx], o, d, closest, 0.0f);  // static scenes only (api.cu rejects motion for this family)
         if (ts_ < closest) {
           closest = ts_;
           id = hidx;
@@ -540,7 +541,7 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_live(const PassBufs pb, int* __
 // fold order of hitable.rs:177-198 but runs every maximal run of analytic spheres as a coherent
 // one-thread-per-ray kernel and every SDF hitable as a pure persistent march kernel.
 __global__ void __launch_bounds__(256) k_extend_spheres(const __grid_constant__ DevScene sc, const PassBufs pb, const int first,
-                                                        const int last, const int init) {
+                                                        const int last, const int init, const int moving) {
   const int ts = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = pb.n_live[ts];
@@ -553,8 +554,11 @@ __global__ void __launch_bounds__(256) k_extend_spheres(const __grid_constant__ 
     const f3 o = mk3(o4.x, o4.y, o4.z), d = mk3(d4.x, d4.y, d4.z);
     float closest = init ? sc.rc.world_radius * 2.0f : d4.w;  // film.rs:556
     int id = init ? -1 : pb.q_key[q];
+    // packets of the extend stage are 4 consecutive live rays (film.rs:612-624); a moving sphere is evaluated at lane 0's time
+    float time0 = o4.w;
+    if (moving && (i & 3)) time0 = pb.o_time[(size_t)ts * pb.R + pb.q_live[(size_t)ts * pb.R + (i & ~3)]].w;
     for (int k = first; k < last; ++k) {
-      const float t = sphere_hit(sc.hit[k], o, d, closest);
+      const float t = sphere_hit(sc.hit[k], o, d, closest, time0);
       if (t < closest) {
         closest = t;
         id = k;
@@ -829,7 +833,7 @@ __global__ void __launch_bounds__(SH_T, 4) k_shade2(const __grid_constant__ DevS
         const bool irrelevant = (c.x == 0.0f || c.x != c.x) && (c.y == 0.0f || c.y != c.y) && (c.z == 0.0f || c.z != c.z);
         if (!irrelevant) {
           for (int k = 0; k < sc.n_hit && vis != 0.0f; ++k)
-            if (sm.hit[k].kind == RAYN_HITABLE_SPHERE) vis = sphere_occluded(sm.hit[k], start, end_point);
+            if (sm.hit[k].kind == RAYN_HITABLE_SPHERE) vis = sphere_occluded(sm.hit[k], start, end_point, 0.0f);
           if (vis != 0.0f) {
             f3 dir = end_point - start;  // TracedSDF::occluded prologue, sdf.rs:26-28
             const float max_dist = mag(dir);
@@ -1055,11 +1059,16 @@ __global__ void __launch_bounds__(128, 8) k_shade_pre(const __grid_constant__ De
   const bool valid = cx.id >= 0;
   warp_add(pb.counters + CNT_SHADE_LANES, valid ? 1 : 0);
   int evals = 0, shadows = 0;
+  const size_t g = (size_t)ts * pb.R + (valid ? cx.id : 0);
+  float4 o4 = make_float4(0, 0, 0, 0);
+  if (valid) o4 = pb.o_time[g];
+  // time of lane 0 of this shading packet (bins pad at the tail, so lane 0 of a non-empty packet is valid): what a
+  // closure-backed Sphere centre is evaluated at in occluded() / get_shading_info() (sphere.rs:29,80; animation.rs:62-67)
+  const float time0 = __shfl_sync(0xffffffffu, o4.w, (threadIdx.x & 31) & ~3);
   if (valid) {
     const RaynHitable& h = sc.hit[cx.obj];
     const RaynMaterial& mat = sc.mat[h.material];
-    const size_t g = (size_t)ts * pb.R + cx.id;
-    const float4 o4 = pb.o_time[g], d4 = pb.d_t[g], r4 = pb.rad[g], t4 = pb.thr[g];
+    const float4 d4 = pb.d_t[g], r4 = pb.rad[g], t4 = pb.thr[g];
     ShadingPoint sp;
     sp.o = mk3(o4.x, o4.y, o4.z);
     sp.d = mk3(d4.x, d4.y, d4.z);
@@ -1082,7 +1091,7 @@ __global__ void __launch_bounds__(128, 8) k_shade_pre(const __grid_constant__ De
       pb.term[g] = ((depth == 0 ? TERM_BACKGROUND : TERM_COLOR) << 30) | ((unsigned)depth << 20) | (unsigned)s;
       pb.q_shade[(size_t)ts * pb.QS + s] = -1;
     } else {
-    shading_info(sc, h, thr, sp, &evals, false);
+    shading_info(sc, h, thr, sp, &evals, false, time0);
     pb.nrm[g] = make_float4(sp.normal.x, sp.normal.y, sp.normal.z, sp.offset_by);
     const f3 radiance = mk3(r4.x, r4.y, r4.z) + bsdf_le(mat, wo) * mk3(t4.x, t4.y, t4.z) * vt;  // :70-71
     pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
@@ -1102,7 +1111,7 @@ __global__ void __launch_bounds__(128, 8) k_shade_pre(const __grid_constant__ De
         if (irrelevant) continue;
         float v = 1.0f;  // analytic spheres first: product of {0,1} factors (hitable.rs:164-168)
         for (int k = 0; k < sc.n_hit && v != 0.0f; ++k)
-          if (sc.hit[k].kind == RAYN_HITABLE_SPHERE) v = sphere_occluded(sc.hit[k], lc.start, lc.end_point);
+          if (sc.hit[k].kind == RAYN_HITABLE_SPHERE) v = sphere_occluded(sc.hit[k], lc.start, lc.end_point, time0);
         if (v == 0.0f) {
           vis &= ~(1u << bit);
           continue;
@@ -1658,7 +1667,7 @@ __global__ void k_kat_occluded(const __grid_constant__ DevScene sc, long long n,
   float acc = 1.0f;
   const f3 a = mk3(s3[3 * i], s3[3 * i + 1], s3[3 * i + 2]), b = mk3(e3[3 * i], e3[3 * i + 1], e3[3 * i + 2]);
   for (int k = 0; k < sc.n_hit; ++k)
-    acc = acc * (sc.hit[k].kind == RAYN_HITABLE_SPHERE ? sphere_occluded(sc.hit[k], a, b) : sdf_occluded(sc.hit[k], sc.rc, a, b, &ev));
+    acc = acc * (sc.hit[k].kind == RAYN_HITABLE_SPHERE ? sphere_occluded(sc.hit[k], a, b, 0.0f) : sdf_occluded(sc.hit[k], sc.rc, a, b, &ev));
   const float fast = test_occluded(sc, a, b, &ev);
   out[i] = acc == fast ? acc : -1.0f;  // -1 flags a disagreement between the two forms
 }

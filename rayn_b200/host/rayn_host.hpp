@@ -28,6 +28,14 @@ struct Vec3 {  // ultraviolet::Vec3, host-side constants only
   void store(float* p) const { p[0] = x, p[1] = y, p[2] = z; }
 };
 using Srgb = Vec3;  // spectrum.rs newtype
+// A Sequenced<Vec3> parameter: constant, or linear in time (stands for the closure `|t| base + velocity * t`,
+// animation.rs:55-68; evaluated at lane 0's time of a packet like every closure-backed WSequenced, :62-67).
+struct Seq3 {
+  Vec3 base, velocity;
+  Seq3(Vec3 b) : base(b) {}  // NOLINT: constants convert implicitly, like `impl Sequenced<Vec3> for Vec3`
+  Seq3(Vec3 b, Vec3 v) : base(b), velocity(v) {}
+};
+inline Seq3 Linear(Vec3 base, Vec3 velocity) { return Seq3(base, velocity); }
 using MaterialHandle = int;
 using CameraHandle = int;
 
@@ -81,10 +89,11 @@ struct Hitable {
   RaynHitable pod{};
 };
 struct Sphere : Hitable {  // sphere.rs:14-20
-  Sphere(Vec3 center, float radius, MaterialHandle material) {
+  Sphere(Seq3 center, float radius, MaterialHandle material) {
     pod.kind = RAYN_HITABLE_SPHERE;
     pod.material = material;
-    center.store(pod.center);
+    center.base.store(pod.center);
+    center.velocity.store(pod.center_velocity);
     pod.radius = radius;
   }
 };
@@ -153,30 +162,35 @@ inline void fov_half(float rx, float ry, float vfov, float* hw, float* hh) {  //
   *hw = (rx / ry) * *hh;
 }
 struct PinholeCamera : Camera {  // camera.rs:52-72
-  PinholeCamera(float rx, float ry, float vfov, Vec3 origin, Vec3 at, Vec3 up) {
+  PinholeCamera(float rx, float ry, float vfov, Seq3 origin, Seq3 at, Seq3 up) {
     pod.kind = RAYN_CAMERA_PINHOLE;
     fov_half(rx, ry, vfov, &pod.half_size[0], &pod.half_size[1]);
     pod.half_pixel_size = pod.half_size[1] / ry;
-    origin.store(pod.origin), at.store(pod.at), up.store(pod.up);
+    origin.base.store(pod.origin), at.base.store(pod.at), up.base.store(pod.up);
+    origin.velocity.store(pod.origin_velocity), at.velocity.store(pod.at_velocity), up.velocity.store(pod.up_velocity);
   }
 };
 struct ThinLensCamera : Camera {  // camera.rs:133-157
-  ThinLensCamera(float rx, float ry, float vfov, float aperture, Vec3 origin, Vec3 at, Vec3 up, Vec3 focus) {
+  ThinLensCamera(float rx, float ry, float vfov, float aperture, Seq3 origin, Seq3 at, Seq3 up, Seq3 focus, float aperture_rate = 0.0f) {
     pod.kind = RAYN_CAMERA_THINLENS;
     fov_half(rx, ry, vfov, &pod.half_size[0], &pod.half_size[1]);
     pod.half_pixel_size = pod.half_size[1] / ry;
     pod.aperture = aperture;
-    origin.store(pod.origin), at.store(pod.at), up.store(pod.up), focus.store(pod.focus);
+    pod.aperture_rate = aperture_rate;
+    origin.base.store(pod.origin), at.base.store(pod.at), up.base.store(pod.up), focus.base.store(pod.focus);
+    origin.velocity.store(pod.origin_velocity), at.velocity.store(pod.at_velocity), up.velocity.store(pod.up_velocity);
+    focus.velocity.store(pod.focus_velocity);
   }
 };
 struct OrthographicCamera : Camera {  // camera.rs:227-241
-  OrthographicCamera(float rx, float ry, float vertical_size, Vec3 origin, Vec3 at, Vec3 up) {
+  OrthographicCamera(float rx, float ry, float vertical_size, Seq3 origin, Seq3 at, Seq3 up) {
     pod.kind = RAYN_CAMERA_ORTHOGRAPHIC;
     const float aspect = rx / ry;
     pod.full_size[0] = vertical_size * aspect, pod.full_size[1] = vertical_size;
     pod.half_size[0] = pod.full_size[0] / 2.0f, pod.half_size[1] = pod.full_size[1] / 2.0f;
     pod.half_pixel_size = (vertical_size / ry) / 2.0f;
-    origin.store(pod.origin), at.store(pod.at), up.store(pod.up);
+    origin.base.store(pod.origin), at.base.store(pod.at), up.base.store(pod.up);
+    origin.velocity.store(pod.origin_velocity), at.velocity.store(pod.at_velocity), up.velocity.store(pod.up_velocity);
   }
 };
 struct CameraStore {  // camera.rs:24-40

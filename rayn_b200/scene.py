@@ -69,6 +69,22 @@ def _arr(x):
     return x.v if isinstance(x, Vec3) else _v3(x)
 
 
+class Linear:
+    """A `Sequenced` parameter that is linear in time: value(t) = base + velocity * t.  Stands for the closure
+    `move |t| base + velocity * t` a rayn scene would pass (animation.rs:55-68); arbitrary closures cannot cross a C ABI.
+    Like every closure-backed WSequenced it is evaluated at lane 0's time for a whole 4-lane packet (animation.rs:62-67)."""
+
+    def __init__(self, base, velocity):
+        self.base, self.velocity = base, velocity
+
+
+def _seq(x):
+    """-> (base[3], velocity[3]) for a constant or Linear Vec3 parameter."""
+    if isinstance(x, Linear):
+        return _arr(x.base), _arr(x.velocity)
+    return _arr(x), np.zeros(3, np.float32)
+
+
 # ---- materials (material.rs) ---------------------------------------------------------------
 class Lambertian:  # material.rs:91-100
     def __init__(self, albedo):
@@ -139,15 +155,16 @@ class MaterialStore:  # material.rs:58-73
 
 
 # ---- hitables (sphere.rs, sdf.rs) --------------------------------------------------------------
-class Sphere:  # sphere.rs:14-20 (constant centre only; closures cannot cross the ABI)
+class Sphere:  # sphere.rs:14-20 (centre: constant or Linear)
     def __init__(self, center, radius, material):
-        self.center, self.radius, self.material = _arr(center), f32(radius), int(material)
+        (self.center, self.center_velocity), self.radius, self.material = _seq(center), f32(radius), int(material)
 
     def flatten(self):
         h = L.RaynHitable()
         h.kind = L.HITABLE_SPHERE
         h.material = self.material
         h.center[:] = self.center.tolist()
+        h.center_velocity[:] = self.center_velocity.tolist()
         h.radius = float(self.radius)
         return h
 
@@ -225,6 +242,14 @@ class SphereLight:  # light.rs:27-34
 
 
 # ---- cameras (camera.rs) ----------------------------------------------------------------------------
+def _store_seq(c, origin, at, up, focus=None):
+    c.origin[:], c.origin_velocity[:] = origin[0].tolist(), origin[1].tolist()
+    c.at[:], c.at_velocity[:] = at[0].tolist(), at[1].tolist()
+    c.up[:], c.up_velocity[:] = up[0].tolist(), up[1].tolist()
+    if focus is not None:
+        c.focus[:], c.focus_velocity[:] = focus[0].tolist(), focus[1].tolist()
+
+
 def _fov_half(resolution, vfov):
     theta = f32(vfov) * f32(math.pi) / f32(180.0)
     # f32::tan -> libm tanf; numpy's float32 tan is 1 ulp off for 30 degrees, so round the double result instead
@@ -239,14 +264,14 @@ class PinholeCamera:  # camera.rs:52-72
         self.res = (f32(resolution[0]), f32(resolution[1]))
         self.half_width, self.half_height = _fov_half(self.res, vfov)
         self.half_pixel_size = self.half_height / self.res[1]
-        self.origin, self.at, self.up = _arr(origin), _arr(at), _arr(up)
+        self.origin, self.at, self.up = _seq(origin), _seq(at), _seq(up)
 
     def flatten(self):
         c = L.RaynCamera()
         c.kind = L.CAMERA_PINHOLE
         c.half_size[:] = [float(self.half_width), float(self.half_height)]
         c.half_pixel_size = float(self.half_pixel_size)
-        c.origin[:], c.at[:], c.up[:] = self.origin.tolist(), self.at.tolist(), self.up.tolist()
+        _store_seq(c, self.origin, self.at, self.up)
         return c
 
 
@@ -255,17 +280,17 @@ class ThinLensCamera:  # camera.rs:133-157
         self.res = (f32(resolution[0]), f32(resolution[1]))
         self.half_width, self.half_height = _fov_half(self.res, vfov)
         self.half_pixel_size = self.half_height / self.res[1]
-        self.aperture = f32(aperture)
-        self.origin, self.at, self.up, self.focus = _arr(origin), _arr(at), _arr(up), _arr(focus)
+        self.aperture, self.aperture_rate = (f32(aperture.base), f32(aperture.velocity)) if isinstance(aperture, Linear) else (f32(aperture), f32(0.0))
+        self.origin, self.at, self.up, self.focus = _seq(origin), _seq(at), _seq(up), _seq(focus)
 
     def flatten(self):
         c = L.RaynCamera()
         c.kind = L.CAMERA_THINLENS
         c.half_size[:] = [float(self.half_width), float(self.half_height)]
         c.half_pixel_size = float(self.half_pixel_size)
-        c.origin[:], c.at[:], c.up[:] = self.origin.tolist(), self.at.tolist(), self.up.tolist()
-        c.focus[:] = self.focus.tolist()
+        _store_seq(c, self.origin, self.at, self.up, self.focus)
         c.aperture = float(self.aperture)
+        c.aperture_rate = float(self.aperture_rate)
         return c
 
 
@@ -275,7 +300,7 @@ class OrthographicCamera:  # camera.rs:227-241
         aspect = self.res[0] / self.res[1]
         self.size = (f32(vertical_size) * aspect, f32(vertical_size))
         self.pixel_size = f32(vertical_size) / self.res[1]
-        self.origin, self.at, self.up = _arr(origin), _arr(at), _arr(up)
+        self.origin, self.at, self.up = _seq(origin), _seq(at), _seq(up)
 
     def flatten(self):
         c = L.RaynCamera()
@@ -283,7 +308,7 @@ class OrthographicCamera:  # camera.rs:227-241
         c.half_size[:] = [float(self.size[0] / f32(2.0)), float(self.size[1] / f32(2.0))]
         c.full_size[:] = [float(self.size[0]), float(self.size[1])]
         c.half_pixel_size = float(self.pixel_size / f32(2.0))
-        c.origin[:], c.at[:], c.up[:] = self.origin.tolist(), self.at.tolist(), self.up.tolist()
+        _store_seq(c, self.origin, self.at, self.up)
         return c
 
 

@@ -171,3 +171,44 @@ def test_device_side_frame_inputs_equal_host_builders(renderer):
     assert_bit_equal(s1.cpu().numpy(), inp.samples_1d, "1-D tables")
     assert_bit_equal(s2.cpu().numpy(), inp.samples_2d, "2-D tables")
     assert_bit_equal(sc.cpu().numpy(), inp.scramble, "scramble")
+
+
+def test_time_varying_sphere_and_camera(renderer, oracle):
+    """linear-in-time sphere centres and camera parameters (real motion blur over the shutter
+    [1/24, 2/24], main.rs:47-49).  The reference evaluates a closure-backed parameter at LANE 0's time of the 4-lane
+    packet (animation.rs:62-67); GPU and oracle must agree bit for bit, and the motion must be visible."""
+    from rayn_b200 import Linear, ThinLensCamera
+    materials, hitables, lights = MaterialStore(), HitableStore(), []
+    sky = materials.add_material(Sky(Srgb(0.3, 0.4, 0.6), Srgb(0.2, 0.3, 0.6) * 0.05))
+    grey = materials.add_material(Dielectric.new_remap(Srgb(0.5, 0.5, 0.5), 0.6))
+    em = materials.add_material(Emissive.new_splat(Srgb(3.0, 2.0, 1.0)))
+    hitables.push(Sphere(Vec3(0, 0, 0), 100.0, sky))
+    hitables.push(TracedSDF(MandelBox(6, BoxFold(1.0), SphereFold(0.5, 1.0), -2.0), grey))
+    hitables.push(Sphere(Linear(Vec3(-3.0, 1.9, 0.0), Vec3(40.0, 0.0, 0.0)), 0.4, grey))   # crosses ~1.7 units during the shutter
+    hitables.push(Sphere(Linear(Vec3(0.0, -2.2, 1.0), Vec3(0.0, 6.0, 0.0)), 0.3, em))
+    lights.append(SphereLight(Vec3(2.5, 2.5, 2.5), 0.2, Srgb(1, 1, 1) * 60.0))
+    cams = CameraStore()
+    res = (48, 40)
+    moving_cam = cams.add_camera(ThinLensCamera(res, 60.0, Linear(0.02, 0.2), Linear(Vec3(-1.0, 0.45, 4.5), Vec3(2.0, 0.0, 0.0)),
+                                                Vec3(0, 0, 0), Linear(Vec3(0, 1, 0), Vec3(0.5, 0, 0)), Linear(Vec3(0, 0, 0), Vec3(0, 1, 0))))
+    still_cam = cams.add_camera(PinholeCamera(res, 60.0, Vec3(-1.0, 0.45, 4.5), Vec3(0, 0, 0), Vec3(0, 1, 0)))
+    world = World(hitables, lights, materials, cams, VolumeParams(None, None))
+    g_move, _ = _both(renderer, oracle, world, moving_cam, res, 2, 3)
+    g_still_cam, _ = _both(renderer, oracle, world, still_cam, res, 2, 3)
+    # same scene with the spheres frozen at t = 0 renders differently: the motion is really applied
+    hitables.items[2] = Sphere(Vec3(-3.0, 1.9, 0.0), 0.4, grey)
+    hitables.items[3] = Sphere(Vec3(0.0, -2.2, 1.0), 0.3, em)
+    g_frozen, _ = _both(renderer, oracle, world, still_cam, res, 2, 3)
+    assert not np.array_equal(g_still_cam["color"], g_frozen["color"])
+    assert not np.array_equal(g_move["color"], g_still_cam["color"])
+    # the non-default kernel families refuse motion instead of silently ignoring it
+    hitables.items[2] = Sphere(Linear(Vec3(-3.0, 1.9, 0.0), Vec3(40.0, 0.0, 0.0)), 0.4, grey)
+    r = Renderer(0, flags=L.FLAG_SIMPLE_MARCH)
+    try:
+        r.upload_scene(world, still_cam)
+        integ = PathTracingIntegrator(1, 2)
+        with pytest.raises(L.RaynError) as e:
+            r.render_host(FrameInputs(48, 40, 1, integ), (16, 16), integ, TR)
+        assert e.value.code == L.RAYN_ERR_UNSUPPORTED
+    finally:
+        r.close()
