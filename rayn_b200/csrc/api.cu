@@ -406,7 +406,6 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
     pb.n_tiles = nt;
     CU(cudaMemcpyAsync(ctx->d_tile_ids, my_tiles.data() + first, nt * sizeof(int), cudaMemcpyHostToDevice, st));
     ctx->stats.passes++;
-    ctx->stats.paths += 0;
     const dim3 g_paths((R + 255) / 256, nt), g_ext((R + 127) / 128, nt), g_shade((QS + 127) / 128, nt);
     timed_begin(ctx, RAYN_K_RAYGEN);
     k_raygen<<<g_paths, 256, 0, st>>>(ctx->scene, fr, pb);

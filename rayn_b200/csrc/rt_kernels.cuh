@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(EXT_T, 8) k_extend_march(const __grid_constant
   bool have = false, first = false, exhausted = false;
   f3 o = {0, 0, 0}, d = {0, 0, 0};
   float closest = 0.0f, t = 0.0f;
-  int steps = 0, evals = 0, rays = 0;
+  int steps = 0, evals = 0;
   size_t q = 0, g = 0;
   int cur_ts = 0, cur_pos = 0, cur_end = 0;
   SdfEval ev;
@@ -630,7 +630,6 @@ __global__ void __launch_bounds__(EXT_T, 8) k_extend_march(const __grid_constant
         closest = d4.w;
         first = true;
         have = true;
-        ++rays;
         if (FLAT) eval_start(ev, s_h, o);
       }
       cur_pos += min(avail, __popc(idle));
@@ -678,7 +677,6 @@ __global__ void __launch_bounds__(EXT_T, 8) k_extend_march(const __grid_constant
       }
     }
   }
-  (void)rays;
   warp_add(pb.counters + CNT_EVALS_EXTEND, evals);
 }
 
