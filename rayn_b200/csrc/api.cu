@@ -384,6 +384,12 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
                                                                  ctx->scene.hit[i].center_velocity[2] != 0.0f);
   if (motion && !v3) return fail(ctx, RAYN_ERR_UNSUPPORTED, "time-varying sphere centres are only supported by the default kernel family (no RAYN_FLAG_SIMPLE_MARCH / BLOCK_POOL)");
   const bool no_flat = (ctx->flags & RAYN_FLAG_FLATTEN) == 0;
+  // persistent kernels: exactly as many CTAs as can be resident (one wave), so every CTA pulls work until the pass is drained
+  int occ_ext = 8, occ_ext_flat = 8, occ_shd = 8, occ_shd_flat = 8;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ext, k_extend_march<false>, EXT_T, 0));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ext_flat, k_extend_march<true>, EXT_T, 0));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_shd, k_shadow<false>, SHD_T, 0));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_shd_flat, k_shadow<true>, SHD_T, 0));
   bool any_bulb = false;
   for (int i = 0; i < n_hit; ++i) any_bulb |= ctx->scene.hit[i].kind == RAYN_HITABLE_MANDELBULB;
   const bool volume_on = ctx->scene.vol.has_scattering != 0 && ctx->scene.n_lights > 0;
@@ -434,9 +440,9 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
           if (e < n_hit) {
             if (n_march++ > 0) CU(cudaMemsetAsync(ctx->d_work_ctr, 0, sizeof(int), st));
             if (ctx->scene.hit[e].kind == RAYN_HITABLE_MANDELBULB && !no_flat)
-              k_extend_march<true><<<ctx->n_sm * 8, EXT_T, 0, st>>>(ctx->scene, pb, thr, e, ctx->d_batch_prefix, ctx->d_work_ctr);
+              k_extend_march<true><<<ctx->n_sm * occ_ext_flat, EXT_T, 0, st>>>(ctx->scene, pb, thr, e, ctx->d_batch_prefix, ctx->d_work_ctr);
             else
-              k_extend_march<false><<<ctx->n_sm * 8, EXT_T, 0, st>>>(ctx->scene, pb, thr, e, ctx->d_batch_prefix, ctx->d_work_ctr);
+              k_extend_march<false><<<ctx->n_sm * occ_ext, EXT_T, 0, st>>>(ctx->scene, pb, thr, e, ctx->d_batch_prefix, ctx->d_work_ctr);
             ctx->stats.launches++;
             ++e;
           }
@@ -468,9 +474,9 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
         if (n_sdf > 0 && ctx->scene.n_lights > 0) {
           timed_begin(ctx, RAYN_K_SHADOW);
           if (any_bulb && !no_flat)
-            k_shadow<true><<<ctx->n_sm * 8, SHD_T, 0, st>>>(ctx->scene, pb, ctx->d_work_ctr + 1);
+            k_shadow<true><<<ctx->n_sm * occ_shd_flat, SHD_T, 0, st>>>(ctx->scene, pb, ctx->d_work_ctr + 1);
           else
-            k_shadow<false><<<ctx->n_sm * 8, SHD_T, 0, st>>>(ctx->scene, pb, ctx->d_work_ctr + 1);
+            k_shadow<false><<<ctx->n_sm * occ_shd, SHD_T, 0, st>>>(ctx->scene, pb, ctx->d_work_ctr + 1);
           timed_end(ctx, RAYN_K_SHADOW);
         }
         timed_begin(ctx, RAYN_K_SHADE_POST);

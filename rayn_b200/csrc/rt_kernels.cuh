@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(256) k_extend_spheres(const __grid_constant__ 
 // varies from 0 to `iterations` (ncu r1v3: 12-14 of 32 lanes active inside the iteration body
 // with evaluation-granular trips).  The arithmetic is the same SdfEval state machine either way.
 template <bool FLAT>
-__global__ void __launch_bounds__(EXT_T, 8) k_extend_march(const __grid_constant__ DevScene sc, const PassBufs pb, const Thr thr,
+__global__ void __launch_bounds__(EXT_T, 10) k_extend_march(const __grid_constant__ DevScene sc, const PassBufs pb, const Thr thr,
                                                            const int hk, const int* __restrict__ batch_prefix, int* __restrict__ work_ctr) {
   __shared__ RaynHitable s_h;  // shared-memory staging of the fractal constants
   if (threadIdx.x == 0) s_h = sc.hit[hk];
@@ -1142,7 +1142,7 @@ __global__ void __launch_bounds__(128, 8) k_shade_pre(const __grid_constant__ De
 // TracedSDF::occluded per lane (sdf.rs:25-57); occlusion clears the owner's bit.
 #define SHD_T 128
 template <bool FLAT>
-__global__ void __launch_bounds__(SHD_T, 8) k_shadow(const __grid_constant__ DevScene sc, const PassBufs pb, int* __restrict__ work_ctr) {
+__global__ void __launch_bounds__(SHD_T, 10) k_shadow(const __grid_constant__ DevScene sc, const PassBufs pb, int* __restrict__ work_ctr) {
   __shared__ RaynHitable s_hit[RAYN_MAX_HITABLES];
   for (int k = threadIdx.x; k < sc.n_hit; k += SHD_T) s_hit[k] = sc.hit[k];
   __syncthreads();
