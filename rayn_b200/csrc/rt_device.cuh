@@ -182,10 +182,19 @@ RT_D void eval_step(SdfEval& e, const RaynHitable& h) {
   } else {
     const float l = h.box_l, nl = -h.box_l;
     f3 p = e.w;
-    // clamped(neg_l, l) = max(neg_l).min(l), then mul_add(two, -p)
-    const float cx = dm::min(dm::max(p.x, nl), l);
-    const float cy = dm::min(dm::max(p.y, nl), l);
-    const float cz = dm::min(dm::max(p.z, nl), l);
+    // clamped(neg_l, l) = max(neg_l).min(l), then mul_add(two, -p).  SSE maxps/minps return the SECOND operand when
+    // unordered; with a constant, non-NaN, non-zero second operand that is exactly fmaxf/fminf for every input
+    // (NaN -> the constant either way; no signed-zero tie is possible), so one FMNMX replaces compare + select.
+    float cx, cy, cz;
+    if (l > 0.0f) {
+      cx = fminf(fmaxf(p.x, nl), l);
+      cy = fminf(fmaxf(p.y, nl), l);
+      cz = fminf(fmaxf(p.z, nl), l);
+    } else {
+      cx = dm::min(dm::max(p.x, nl), l);
+      cy = dm::min(dm::max(p.y, nl), l);
+      cz = dm::min(dm::max(p.z, nl), l);
+    }
     p.x = dm::fma(cx, 2.0f, -p.x);
     p.y = dm::fma(cy, 2.0f, -p.y);
     p.z = dm::fma(cz, 2.0f, -p.z);
