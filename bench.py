@@ -243,10 +243,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    clocks = ClockSampler(local_rank) if rank == 0 else None  # started before warm-up (nvidia-smi needs ~0.3 s to emit its first line); every sample is under load
     for _ in range(args.warmup):
         step_resident()
     barrier()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
     lib_ms = 0.0
