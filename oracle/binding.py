@@ -42,6 +42,9 @@ def lib():
                                               C.c_float, C.c_int32, fp]
         l.rayn_oracle_kat_occluded.argtypes = [C.POINTER(L.RaynSceneDesc), C.c_int64, fp, fp, fp]
         l.rayn_oracle_kat_closest_hit.argtypes = [C.POINTER(L.RaynSceneDesc), C.c_int32, C.c_int64, fp, fp, fp, C.POINTER(C.c_int32)]
+        l.rayn_oracle_kat_light_sample.argtypes = [C.POINTER(L.RaynLight), C.c_int64, fp, fp, fp, fp, fp]
+        l.rayn_oracle_kat_light_sample_volume.argtypes = [C.POINTER(L.RaynLight), C.c_int64, fp, fp, fp, fp, fp, fp]
+        l.rayn_oracle_kat_bsdf.argtypes = [C.POINTER(L.RaynMaterial), C.c_int64, fp, fp, fp, fp, fp, fp, fp, fp]
         l.rayn_oracle_film_postprocess.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(L.RaynFilmPlanes), C.c_void_p]
         if l.rayn_oracle_selfcheck() != 0:
             raise RuntimeError("oracle was built with FP contraction on: rebuild with -ffp-contract=off")
@@ -135,3 +138,27 @@ def film_postprocess(mode, width, height, planes):
     out = np.zeros((height, width, L.POST_BYTES[mode]), np.uint8)
     lib().rayn_oracle_film_postprocess(mode, width, height, C.byref(p), out.ctypes.data)
     return out
+
+
+def kat_light_sample(light, s0, s1, p):
+    s0, s1 = np.ascontiguousarray(s0, np.float32), np.ascontiguousarray(s1, np.float32)
+    p = np.ascontiguousarray(p, np.float32).reshape(-1, 3)
+    pt, pdf = np.empty_like(p), np.empty(len(p), np.float32)
+    lib().rayn_oracle_kat_light_sample(C.byref(light), len(p), _f(s0), _f(s1), _f(p), _f(pt), _f(pdf))
+    return pt, pdf
+
+
+def kat_light_sample_volume(light, sample, o, d, t_max):
+    sample, t_max = np.ascontiguousarray(sample, np.float32), np.ascontiguousarray(t_max, np.float32)
+    o, d = np.ascontiguousarray(o, np.float32).reshape(-1, 3), np.ascontiguousarray(d, np.float32).reshape(-1, 3)
+    t, pdf = np.empty(len(o), np.float32), np.empty(len(o), np.float32)
+    lib().rayn_oracle_kat_light_sample_volume(C.byref(light), len(o), _f(sample), _f(o), _f(d), _f(t_max), _f(t), _f(pdf))
+    return t, pdf
+
+
+def kat_bsdf(mat, normals, wo, s1d, u4):
+    n3, w3 = np.ascontiguousarray(normals, np.float32).reshape(-1, 3), np.ascontiguousarray(wo, np.float32).reshape(-1, 3)
+    s1d, u4 = np.ascontiguousarray(s1d, np.float32), np.ascontiguousarray(u4, np.float32).reshape(-1, 4)
+    wi, f, fe, pdf = np.empty_like(n3), np.empty_like(n3), np.empty_like(n3), np.empty(len(n3), np.float32)
+    lib().rayn_oracle_kat_bsdf(C.byref(mat), len(n3), _f(n3), _f(w3), _f(s1d), _f(u4), _f(wi), _f(f), _f(pdf), _f(fe))
+    return wi, f, pdf, fe

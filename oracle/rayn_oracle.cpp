@@ -1218,6 +1218,59 @@ int32_t rayn_oracle_kat_occluded(const RaynSceneDesc* scene, int64_t n, const fl
   return RAYN_OK;
 }
 
+// SphereLight::sample (light.rs:38-72): out_point3[n*3], out_pdf[n]
+int32_t rayn_oracle_kat_light_sample(const RaynLight* light, int64_t n, const float* s0, const float* s1, const float* p3, float* out_point3,
+                                     float* out_pdf) {
+  for (int64_t i = 0; i < n; i += 4) {
+    V3 pt, li;
+    F4 pdf;
+    light_sample(*light, load_f_packet(s0, i, n), load_f_packet(s1, i, n), load_v3_packet(p3, i, n), &pt, &li, &pdf);
+    store_f_packet(out_pdf, i, n, pdf);
+    for (int l = 0; l < 4 && i + l < n; ++l) {
+      out_point3[3 * (i + l)] = pt.x[l], out_point3[3 * (i + l) + 1] = pt.y[l], out_point3[3 * (i + l) + 2] = pt.z[l];
+    }
+  }
+  return RAYN_OK;
+}
+// SphereLight::sample_volume_scattering (light.rs:75-102): equi-angular distance + pdf
+int32_t rayn_oracle_kat_light_sample_volume(const RaynLight* light, int64_t n, const float* sample, const float* o3, const float* d3,
+                                            const float* t_max, float* out_t, float* out_pdf) {
+  for (int64_t i = 0; i < n; i += 4) {
+    F4 t, pdf;
+    light_sample_volume(*light, load_f_packet(sample, i, n), load_v3_packet(o3, i, n), load_v3_packet(d3, i, n), load_f_packet(t_max, i, n), &t, &pdf);
+    store_f_packet(out_t, i, n, t);
+    store_f_packet(out_pdf, i, n, pdf);
+  }
+  return RAYN_OK;
+}
+// BSDF::scatter + BSDF::f (material.rs): for unit normals n3 and outgoing wo3, samples (s1d, u0..u3):
+// out_wi3, out_f3 (the scatter event's f), out_pdf, out_feval3 = bsdf.f(wo, wi, n) as the integrator calls it.
+int32_t rayn_oracle_kat_bsdf(const RaynMaterial* mat, int64_t n, const float* n3, const float* wo3, const float* s1d, const float* u4,
+                             float* out_wi3, float* out_f3, float* out_pdf, float* out_feval3) {
+  for (int64_t i = 0; i < n; i += 4) {
+    ShadingPoint sp;
+    sp.normal = load_v3_packet(n3, i, n);
+    sp.basis = onb(sp.normal);
+    V3 wo = load_v3_packet(wo3, i, n);
+    F4 u[4];
+    for (int k = 0; k < 4; ++k) {
+      float tmp[4];
+      for (int l = 0; l < 4; ++l) tmp[l] = u4[4 * (i + l < n ? i + l : n - 1) + k];
+      u[k] = load4(tmp);
+    }
+    Scatter se = bsdf_scatter(*mat, wo, sp, load_f_packet(s1d, i, n), u);
+    V3 fe = bsdf_f(*mat, wo, se.wi, sp.normal);
+    store_f_packet(out_pdf, i, n, se.pdf);
+    for (int l = 0; l < 4 && i + l < n; ++l) {
+      const int64_t j = i + l;
+      out_wi3[3 * j] = se.wi.x[l], out_wi3[3 * j + 1] = se.wi.y[l], out_wi3[3 * j + 2] = se.wi.z[l];
+      out_f3[3 * j] = se.f.x[l], out_f3[3 * j + 1] = se.f.y[l], out_f3[3 * j + 2] = se.f.z[l];
+      out_feval3[3 * j] = fe.x[l], out_feval3[3 * j + 1] = fe.y[l], out_feval3[3 * j + 2] = fe.z[l];
+    }
+  }
+  return RAYN_OK;
+}
+
 int32_t rayn_oracle_kat_closest_hit(const RaynSceneDesc* scene, int32_t depth, int64_t n, const float* origins3,
                                     const float* dirs3, float* out_t, int32_t* out_obj) {
   World w{scene};
