@@ -332,6 +332,18 @@ int32_t rayn_b200_kat_closest_hit(RaynContext* ctx, int32_t depth, int64_t n,
                                   const float* origins3, const float* dirs3, float* out_t,
                                   int32_t* out_obj);
 
+/* SphereLight::sample (light.rs:38-72) and ::sample_volume_scattering (:75-102) per lane */
+int32_t rayn_b200_kat_light_sample(RaynContext* ctx, const RaynLight* light, int64_t n, const float* s0,
+                                   const float* s1, const float* points3, float* out_point3, float* out_pdf);
+int32_t rayn_b200_kat_light_sample_volume(RaynContext* ctx, const RaynLight* light, int64_t n,
+                                          const float* sample, const float* origins3, const float* dirs3,
+                                          const float* t_max, float* out_t, float* out_pdf);
+/* BSDF::scatter + BSDF::f (material.rs): normals3/wo3 unit vectors, s1d[n], u4[4n] ->
+ * out_wi3, out_f3 (scatter event f), out_pdf, out_feval3 = bsdf.f(wo, wi, n) as integrator.rs:230 calls it */
+int32_t rayn_b200_kat_bsdf(RaynContext* ctx, const RaynMaterial* mat, int64_t n, const float* normals3,
+                           const float* wo3, const float* s1d, const float* u4, float* out_wi3,
+                           float* out_f3, float* out_pdf, float* out_feval3);
+
 /* Packet-order debugging: when enabled, render_frame records for every depth
  * and tile the shading queue (path id per slot, -1 = padding) into an internal host log. */
 int32_t rayn_b200_debug_enable_queue_log(RaynContext* ctx, int32_t enable);

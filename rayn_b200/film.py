@@ -176,6 +176,29 @@ class Renderer:
                                                     obj.ctypes.data_as(C.POINTER(C.c_int32))), self._ctx)
         return t, obj
 
+    def kat_light_sample(self, light, s0, s1, p):
+        s0, s1 = np.ascontiguousarray(s0, np.float32), np.ascontiguousarray(s1, np.float32)
+        p = np.ascontiguousarray(p, np.float32).reshape(-1, 3)
+        pt, pdf = np.empty_like(p), np.empty(len(p), np.float32)
+        L.check(self._lib.rayn_b200_kat_light_sample(self._ctx, C.byref(light), len(p), _fptr(s0), _fptr(s1), _fptr(p), _fptr(pt), _fptr(pdf)), self._ctx)
+        return pt, pdf
+
+    def kat_light_sample_volume(self, light, sample, o, d, t_max):
+        sample, t_max = np.ascontiguousarray(sample, np.float32), np.ascontiguousarray(t_max, np.float32)
+        o, d = np.ascontiguousarray(o, np.float32).reshape(-1, 3), np.ascontiguousarray(d, np.float32).reshape(-1, 3)
+        t, pdf = np.empty(len(o), np.float32), np.empty(len(o), np.float32)
+        L.check(self._lib.rayn_b200_kat_light_sample_volume(self._ctx, C.byref(light), len(o), _fptr(sample), _fptr(o), _fptr(d), _fptr(t_max),
+                                                            _fptr(t), _fptr(pdf)), self._ctx)
+        return t, pdf
+
+    def kat_bsdf(self, mat, normals, wo, s1d, u4):
+        n3, w3 = np.ascontiguousarray(normals, np.float32).reshape(-1, 3), np.ascontiguousarray(wo, np.float32).reshape(-1, 3)
+        s1d, u4 = np.ascontiguousarray(s1d, np.float32), np.ascontiguousarray(u4, np.float32).reshape(-1, 4)
+        wi, f, fe, pdf = np.empty_like(n3), np.empty_like(n3), np.empty_like(n3), np.empty(len(n3), np.float32)
+        L.check(self._lib.rayn_b200_kat_bsdf(self._ctx, C.byref(mat), len(n3), _fptr(n3), _fptr(w3), _fptr(s1d), _fptr(u4), _fptr(wi), _fptr(f),
+                                             _fptr(pdf), _fptr(fe)), self._ctx)
+        return wi, f, pdf, fe
+
     def enable_queue_log(self, on=True):
         L.check(self._lib.rayn_b200_debug_enable_queue_log(self._ctx, 1 if on else 0), self._ctx)
 

@@ -348,3 +348,35 @@ def test_full_size_config_tile_sample_matches_oracle(oracle, n, k):
     assert g["alpha"].min() >= 0 and g["alpha"].max() <= 1.0
     covered = (g["alpha"] > 0) | (g["background"].reshape(-1, 3).sum(1) > 0)
     assert covered.mean() > 0.999  # every camera ray ends on the sky sphere or the fractal
+
+
+# ---- K4 stage tests: light sampling and BSDFs, host vs device -------------------------
+def test_light_and_bsdf_stages_bit_equal(renderer, oracle):
+    from rayn_b200.scene import Dielectric, Lambertian, SphereLight, Srgb, Vec3
+    from test_cpu_closed_form import _hemisphere_inputs
+    rng = np.random.default_rng(21)
+    n = 50_000
+    light = SphereLight(Vec3(1.2, -1.2, 1.2), 0.15, Srgb(1.5, 4.5, 3.0)).flatten()
+    p = rng.uniform(-2.5, 2.5, size=(n, 3)).astype(np.float32)
+    s0, s1 = rng.random(n, dtype=np.float32), rng.random(n, dtype=np.float32)
+    s0[:3] = [0.0, 1.0, 0.5]
+    p[3] = light.pos[:]  # degenerate: shading point at the light centre
+    gpt, gpdf = renderer.kat_light_sample(light, s0, s1, p)
+    opt, opdf = oracle.kat_light_sample(light, s0, s1, p)
+    assert_bit_equal(gpt, opt, "light sample point")
+    assert_bit_equal(gpdf, opdf, "light sample pdf")
+    o = rng.uniform(-3, 3, size=(n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3)); d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    tm = rng.uniform(0.1, 50, n).astype(np.float32)
+    gt, gp = renderer.kat_light_sample_volume(light, s0, o, d, tm)
+    ot, op = oracle.kat_light_sample_volume(light, s0, o, d, tm)
+    assert_bit_equal(gt, ot, "equi-angular t")
+    assert_bit_equal(gp, op, "equi-angular pdf")
+    nrm, wo, s1d, u4 = _hemisphere_inputs(n, 5)
+    u4[0] = [0.5, 0.5, 0.0, 0.0]  # concentric map (0,0) guard, math.rs:206-207
+    for mat in (Lambertian(Srgb(0.6, 0.4, 0.2)).flatten(), Dielectric.new_remap(Srgb(0.2, 0.2, 0.2), 0.6).flatten(),
+                Dielectric(Srgb(0.9, 0.9, 0.9), 300.0).flatten()):
+        g = renderer.kat_bsdf(mat, nrm, wo, s1d, u4)
+        r = oracle.kat_bsdf(mat, nrm, wo, s1d, u4)
+        for a, b, what in zip(g, r, ("wi", "f", "pdf", "f(wo,wi,n)")):
+            assert_bit_equal(a, b, f"bsdf kind {mat.kind} {what}")
