@@ -31,6 +31,7 @@ struct RaynContext {
   int64_t cap_paths = 0;  // requested paths per pass
   // pass buffers
   int64_t alloc_paths = 0, alloc_q = 0, alloc_seg = 0;
+  int alloc_lc_ns = 0;
   int alloc_tiles = 0;
   PassBufs pb;
   int* d_tile_ids = nullptr;
@@ -90,19 +91,21 @@ static void free_pass(RaynContext* c) {
   cudaFree(c->d_tile_ids);
   cudaFree(c->d_batch_prefix);
   c->d_batch_prefix = nullptr;
-  cudaFree(p.nrm), cudaFree(p.vis), cudaFree(p.seg_a), cudaFree(p.seg_b), cudaFree(p.seg_owner);
+  cudaFree(p.nrm), cudaFree(p.vis), cudaFree(p.seg_a), cudaFree(p.seg_b), cudaFree(p.seg_owner), cudaFree(p.lc_c), cudaFree(p.lc_t);
   unsigned long long* counters = p.counters;
   memset(&p, 0, sizeof p);
   p.counters = counters;
   c->d_tile_ids = nullptr;
   c->alloc_paths = c->alloc_q = c->alloc_seg = 0;
+  c->alloc_lc_ns = 0;
   c->alloc_tiles = 0;
 }
 
-static int32_t ensure_pass(RaynContext* ctx, int n_tiles, int R, int QS, int seg_per_path) {
+static int32_t ensure_pass(RaynContext* ctx, int n_tiles, int R, int QS, int seg_per_path, int lc_ns) {
   const int64_t need_paths = (int64_t)n_tiles * R, need_q = (int64_t)n_tiles * QS;
   const int64_t need_seg = need_paths * seg_per_path;
-  if (need_paths <= ctx->alloc_paths && need_q <= ctx->alloc_q && n_tiles <= ctx->alloc_tiles && need_seg <= ctx->alloc_seg) return RAYN_OK;
+  if (need_paths <= ctx->alloc_paths && need_q <= ctx->alloc_q && n_tiles <= ctx->alloc_tiles && need_seg <= ctx->alloc_seg && lc_ns <= ctx->alloc_lc_ns)
+    return RAYN_OK;
   free_pass(ctx);
   PassBufs& p = ctx->pb;
   CU(cudaMalloc(&p.o_time, need_paths * sizeof(float4)));
@@ -128,6 +131,11 @@ static int32_t ensure_pass(RaynContext* ctx, int n_tiles, int R, int QS, int seg
   }
   p.seg_cap = need_seg;
   ctx->alloc_seg = need_seg;
+  if (lc_ns > 0) {
+    CU(cudaMalloc(&p.lc_c, need_paths * lc_ns * sizeof(float4)));
+    if (lc_ns > 4) CU(cudaMalloc(&p.lc_t, need_paths * 8 * sizeof(float)));
+  }
+  ctx->alloc_lc_ns = lc_ns;
   ctx->alloc_paths = need_paths;
   ctx->alloc_q = need_q;
   ctx->alloc_tiles = n_tiles;
@@ -395,10 +403,12 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
   const bool volume_on = ctx->scene.vol.has_scattering != 0 && ctx->scene.n_lights > 0;
   const int seg_per_path = v3 ? (volume_on ? 4 * (1 + vm) : 4) * n_sdf : 0;  // worst case shadow segments per path per depth
   if (v3 && volume_on) tiles_per_pass = std::max(1, tiles_per_pass / 3);
-  int32_t rc = ensure_pass(ctx, tiles_per_pass, R, QS, seg_per_path);
+  const int lc_ns = v3 ? (volume_on ? 4 * (1 + vm) : 4) : 0;  // stored light contributions per path per depth
+  int32_t rc = ensure_pass(ctx, tiles_per_pass, R, QS, seg_per_path, lc_ns);
   if (rc) return rc;
   PassBufs pb = ctx->pb;
   pb.R = R, pb.QS = QS, pb.tile_ids = ctx->d_tile_ids;
+  pb.lc_ns = lc_ns;
   pb.seg_count = ctx->d_work_ctr + 2;
   CU(cudaMemsetAsync(pb.counters, 0, 8 * sizeof(unsigned long long), st));
   int np = 2;

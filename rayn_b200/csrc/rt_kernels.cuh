@@ -56,6 +56,9 @@ struct PassBufs {
   int* seg_owner;     // [seg_cap] path index g
   int* seg_count;     // [1] segments pushed this depth
   long long seg_cap;
+  float4* lc_c;       // [paths * lc_ns] unoccluded light contribution c.xyz and its denominator (pdf), per light sample of this depth
+  float* lc_t;        // [paths * 8] volume rounds only: transmission to the scatter point (integrator.rs:122-126)
+  int lc_ns;          // light samples per path per depth: 4, or 4 * (1 + vm) with volumetrics
 };
 
 enum { CNT_EXTEND_RAYS = 0, CNT_SHADE_LANES = 1, CNT_SHADOW_RAYS = 2, CNT_EVALS_EXTEND = 3, CNT_EVALS_SHADOW = 4 };
@@ -962,9 +965,9 @@ __global__ void __launch_bounds__(SH_T, 4) k_shade2(const __grid_constant__ DevS
 // v3 shading: k_shade_pre -> k_shadow (persistent) -> k_shade_post.
 // The block-level pool of k_shade2 still drains to a tail every round; v3 pushes the shadow
 // segments of the whole pass into one HBM queue and marches it with resident warps that pull
-// 32-segment batches from a global counter.  pre and post both evaluate light_contrib() - the
-// same instruction sequence on the same inputs, so the same bits - which costs a few hundred
-// cheap instructions per sample and saves storing 20 B x 12 samples per path.
+// 64-segment batches from a global counter.  pre evaluates light_contrib() once per light sample and
+// stores the unoccluded contribution (c.xyz, pdf [, transmission]) per path; post multiplies by the
+// visibility bit and accumulates in the reference's order (HBM is idle here, ALU issue is not).
 // ==========================================================================================
 struct LightContrib {
   f3 start, end_point, c;
@@ -1104,6 +1107,8 @@ __global__ void __launch_bounds__(128, 8) k_shade_pre(const __grid_constant__ De
                                               samp2(fr, 1, cx.sample, cx.scramble, set), vol_sample, has_ext, neg_rho_t);
         ++shadows;
         const int bit = round * 4 + i;
+        pb.lc_c[g * pb.lc_ns + bit] = make_float4(lc.c.x, lc.c.y, lc.c.z, lc.den);  // k_shade_post folds these in; HBM is idle, ALU is not
+        if (round > 0) pb.lc_t[g * 8 + (bit - 4)] = lc.trans;
         // a contribution that is (+-0 | NaN) in every channel is the same bits for visibility 0 and 1
         const bool irrelevant = (lc.c.x == 0.0f || lc.c.x != lc.c.x) && (lc.c.y == 0.0f || lc.c.y != lc.c.y) && (lc.c.z == 0.0f || lc.c.z != lc.c.z);
         if (irrelevant) continue;
@@ -1265,20 +1270,17 @@ __global__ void __launch_bounds__(128, 8) k_shade_post(const __grid_constant__ D
   const int n_rounds = nl > 0 ? 1 + (scat ? fr.vm : 0) : 0;
   const unsigned vis = pb.vis[g];
   for (int round = (recv ? 0 : 1); round < n_rounds; ++round) {
-    const unsigned wr = round == 0 ? cx.w0 : (round == 1 ? cx.w1 : cx.w2);
-    const float vol_sample = round == 0 ? 0.0f : samp1(fr, cx.sample, cx.scramble, cx.set1 + 1);
     const float correction = round == 0 ? (float)nl / 4.0f : (float)nl / 4.0f / (float)fr.vm;  // :79-80,104-108
-#pragma unroll 1
+#pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int set = round == 0 ? cx.set2 + i : cx.set2 + 4 + 4 * (round - 1) + i;
-      const LightContrib lc = light_contrib(sc.light[(wr >> (8 * i)) & 0xffu], mat, sp, wo, round, samp2(fr, 0, cx.sample, cx.scramble, set),
-                                            samp2(fr, 1, cx.sample, cx.scramble, set), vol_sample, has_ext, neg_rho_t);
-      const float occluded = (vis >> (round * 4 + i)) & 1u ? 1.0f : 0.0f;
-      const f3 contrib = lc.c * occluded / lc.den;
+      const int bit = round * 4 + i;
+      const float4 c4 = pb.lc_c[g * pb.lc_ns + bit];  // li * f * transmission and pdf, written by k_shade_pre
+      const float occluded = (vis >> bit) & 1u ? 1.0f : 0.0f;
+      const f3 contrib = mk3(c4.x, c4.y, c4.z) * occluded / c4.w;  // :239 / :278
       if (round == 0)
         radiance = radiance + contrib * throughput * correction * vt;  // :91-92
       else
-        radiance = radiance + contrib * throughput * correction * sc.vol.coeff_scattering * lc.trans;  // :128-129
+        radiance = radiance + contrib * throughput * correction * sc.vol.coeff_scattering * pb.lc_t[g * 8 + (bit - 4)];  // :128-129
     }
   }
   if (recv) {  // :134-188
