@@ -162,3 +162,8 @@ def kat_bsdf(mat, normals, wo, s1d, u4):
     wi, f, fe, pdf = np.empty_like(n3), np.empty_like(n3), np.empty_like(n3), np.empty(len(n3), np.float32)
     lib().rayn_oracle_kat_bsdf(C.byref(mat), len(n3), _f(n3), _f(w3), _f(s1d), _f(u4), _f(wi), _f(f), _f(pdf), _f(fe))
     return wi, f, pdf, fe
+
+
+def set_decoupled_lights(on):
+    """TEST-ONLY: per-lane instead of per-packet surface-NEE light choice.  Always reset to False."""
+    lib().rayn_oracle_set_decoupled_lights(1 if on else 0)

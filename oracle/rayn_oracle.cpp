@@ -742,6 +742,12 @@ inline V3 volume_sample_one_light(const World& w, int light_idx, F4 ls0, F4 ls1,
   return li * f * transmission * occluded / (vol_pdf * light_pdf);
 }
 
+// TEST-ONLY switch: when set, every lane draws its four surface-NEE lights from its OWN sample
+// (index_i = floor(fract(s + i/4) * L)) instead of taking one index from each packet lane.  Both estimators are unbiased
+// with the same L/4 weight, so their high-spp means must agree; this guards the correction factor independently of the
+// bit-parity tests (which compare two statements of the same formula).  Never set on a parity or timing path.
+static int g_decoupled_lights = 0;
+
 enum Channel { CH_COLOR = 0, CH_ALPHA = 1, CH_BACKGROUND = 2, CH_NORMAL = 3 };
 struct OutSample {
   uint32_t tx, ty;
@@ -772,8 +778,20 @@ void integrate(const World& w, int max_bounces, int volume_marches, const F4* s1
   if (receives_light(mat) && nl > 0) {
     F4 correction = splat((float)nl / 4.0f);
     for (int i = 0; i < 4; ++i) {
-      int li_idx = light_index(s1d[0][i], nl);
-      V3 li = surface_sample_one_light(w, li_idx, s2d[0 + i * 2], s2d[1 + i * 2], sp, mat);
+      V3 li;
+      if (!g_decoupled_lights) {
+        int li_idx = light_index(s1d[0][i], nl);
+        li = surface_sample_one_light(w, li_idx, s2d[0 + i * 2], s2d[1 + i * 2], sp, mat);
+      } else {  // per-lane light choice: evaluate the packet once per lane and keep that lane's result
+        float lx[4], ly[4], lz[4];
+        for (int lane = 0; lane < 4; ++lane) {
+          float u = s1d[0][lane] + 0.25f * (float)i;
+          u = u - floorf(u);
+          V3 one = surface_sample_one_light(w, light_index(u, nl), s2d[0 + i * 2], s2d[1 + i * 2], sp, mat);
+          lx[lane] = one.x[lane], ly[lane] = one.y[lane], lz[lane] = one.z[lane];
+        }
+        li = {load4(lx), load4(ly), load4(lz)};
+      }
       sp.ray.radiance = sp.ray.radiance + li * sp.ray.throughput * correction * volume_transmission;
       cnt.shadow_rays += 4;
     }
@@ -1070,6 +1088,7 @@ bool fp_contract_is_off() {
 extern "C" {
 
 int32_t rayn_oracle_selfcheck(void) { return fp_contract_is_off() ? 0 : 1; }
+void rayn_oracle_set_decoupled_lights(int32_t on) { g_decoupled_lights = on; }  // TEST-ONLY, see g_decoupled_lights
 
 // Renders tiles with (tile_index % tile_stride) == tile_offset AND ((tile_index / tile_stride) % subsample_k) == 0.
 // Planes are host pointers; untouched pixels keep their previous contents.

@@ -94,3 +94,40 @@ def test_dielectric_lobe_selection_and_reference_quirk(oracle):
     assert (f[spec][~below] > 0).all()                                        # the rest of the (wide, exponent 8.68) lobe keeps its Phong value
     assert (pdf > 0).all() and np.isfinite(pdf).all()
     assert np.isfinite(fe).all() and (fe >= 0).all()
+
+
+def test_packet_coupled_light_selection_is_unbiased(oracle):
+    """rayn picks the 4 NEE lights of a shading packet from the 4 lanes' samples and applies each to all lanes
+    with weight L/4 (integrator.rs:76-93).  A per-lane choice with the same weight is also unbiased, so the two
+    high-spp means must agree within Monte-Carlo error; a wrong correction factor would shift one of them."""
+    from rayn_b200 import (CameraStore, HitableStore, Lambertian, MaterialStore, PathTracingIntegrator, PinholeCamera, Sky, Sphere, SphereLight,
+                           VolumeParams, World, configs)
+    from rayn_b200.film import FrameInputs
+    materials, hitables = MaterialStore(), HitableStore()
+    sky = materials.add_material(Sky(Srgb(0, 0, 0), Srgb(0, 0, 0)))
+    white = materials.add_material(Lambertian(Srgb(0.7, 0.7, 0.7)))
+    hitables.push(Sphere(Vec3(0, 0, 0), 100.0, sky))
+    hitables.push(Sphere(Vec3(0, 0, 0), 1.0, white))
+    lights = [SphereLight(Vec3(2.0, 2.0, 2.0), 0.2, Srgb(30, 5, 5)), SphereLight(Vec3(-2.5, 0.5, 2.0), 0.3, Srgb(5, 30, 5)),
+              SphereLight(Vec3(0.0, -2.5, 2.5), 0.25, Srgb(5, 5, 30))]
+    cams = CameraStore()
+    cam = cams.add_camera(PinholeCamera((16, 16), 30.0, Vec3(0.0, 0.0, 5.0), Vec3(0, 0, 0), Vec3(0, 1, 0)))
+    world = World(hitables, lights, materials, cams, VolumeParams(None, None))
+    integ = PathTracingIntegrator(0, 2)  # direct lighting only: Color = NEE at depth 0
+    inp = FrameInputs(16, 16, 512, integ)  # 2048 spp
+    tr = configs.frame_time_range(1)
+    a, _ = oracle.render(world, cam, inp, (16, 16), integ, tr)
+    oracle.set_decoupled_lights(True)
+    try:
+        b, _ = oracle.render(world, cam, inp, (16, 16), integ, tr)
+    finally:
+        oracle.set_decoupled_lights(False)
+    ca, cb = a["color"].reshape(-1, 3), b["color"].reshape(-1, 3)
+    lit = ca.sum(1) > 0.05 * ca.sum(1).max()
+    assert lit.sum() > 60
+    assert not np.array_equal(ca, cb)                                         # genuinely different estimators
+    assert np.allclose(ca[lit].mean(0), cb[lit].mean(0), rtol=0.01)           # same mean per colour channel (each light has its own colour)
+    per_pixel = np.abs(ca[lit] - cb[lit]).sum(1) / ca[lit].sum(1)
+    assert np.median(per_pixel) < 0.05
+    again, _ = oracle.render(world, cam, inp, (16, 16), integ, tr)            # switch is off again: bit-identical to the first render
+    assert np.array_equal(again["color"], a["color"])
