@@ -209,8 +209,8 @@ typedef struct RaynConfig {
 
 #define RAYN_FLAG_TIMING 1       /* record per-kernel CUDA-event times into RaynStats      */
 #define RAYN_FLAG_SIMPLE_MARCH 2 /* v0: one-thread-per-ray march kernels (no lane refill)  */
-#define RAYN_FLAG_BLOCK_POOL 4   /* v2: per-block refill / shadow pool instead of the
-                                    pass-wide persistent march kernels (v3, default)       */
+#define RAYN_FLAG_BLOCK_POOL 4   /* v2: per-block refill / shadow pool instead of the default
+                                    pass-wide persistent march kernels                     */
 
 #define RAYN_FLAG_FLATTEN 8      /* experimental: iteration-granular march trips for the Mandelbulb
                                     (measured slower than evaluation-granular trips; off by default) */
