@@ -30,9 +30,13 @@
 extern "C" {
 #endif
 
-#define RAYN_B200_ABI_VERSION 1
+#define RAYN_B200_ABI_VERSION 2
 
-/* ---- limits (fixed so the scene fits a kernel-parameter block) ------------------- */
+/* ---- limits (fixed so the scene fits a kernel-parameter block) -------------------
+ * CONTRACT CHANGE vs the reference: its stores are unbounded `Vec<Box<dyn ..>>` (src/hitable.rs:143,
+ * src/material.rs:58, src/world.rs:7-13).  Here the whole scene rides in the 4 KB kernel-parameter constant bank
+ * (warp-uniform operands then cost no load), which caps the counts; setup.rs needs 7 / 4 / 5.  upload_scene returns
+ * RAYN_ERR_INVALID_ARG beyond these.                                                                              */
 #define RAYN_MAX_HITABLES 16
 #define RAYN_MAX_MATERIALS 16
 #define RAYN_MAX_LIGHTS 16
@@ -46,7 +50,8 @@ typedef enum RaynStatus {
   RAYN_ERR_CUDA = 3,
   RAYN_ERR_OOM = 4,
   RAYN_ERR_NO_SCENE = 5,
-  RAYN_ERR_NO_DEVICE = 6
+  RAYN_ERR_NO_DEVICE = 6,
+  RAYN_ERR_NCCL = 7      /* NCCL missing (dlopen) or a collective failed                    */
 } RaynStatus;
 
 /* ---- Hitable (src/hitable.rs:8-18) ------------------------------------------------ */
@@ -125,11 +130,15 @@ typedef struct RaynCamera {
   float focus[3];        /* thin lens: focus point                                         */
   float aperture;        /* thin lens                                                      */
   /* linear-in-time camera parameters, same closure semantics as RaynHitable.center_velocity
-   * (camera.rs:90-92,177-182,258-260 sample origin/at/up/focus/aperture at the packet's time)      */
+   * (camera.rs:90-92,177-182,258-260 sample origin/at/up/focus at the packet's time): a closure-backed
+   * WSequenced<Wec3> is evaluated at LANE 0's time (animation.rs:62-67).                                  */
   float origin_velocity[3];
   float at_velocity[3];
   float up_velocity[3];
   float focus_velocity[3];
+  /* EXTENSION, no reference counterpart: aperture(t) = aperture + aperture_rate * t0 (lane-0 time).  The reference
+   * implements closure-backed WSequenced only for Fn(f32)->Vec3; an f32 parameter can only be a constant there
+   * (impl_wsequenced_for_sequenced, animation.rs:51-53).  Keep 0 for reference behaviour.                       */
   float aperture_rate;
 } RaynCamera;
 
@@ -192,7 +201,9 @@ typedef struct RaynFrameDesc {
   int32_t n_tile_list;
 } RaynFrameDesc;
 
-/* ---- Film channel planes (src/film.rs:103-120), row-major, y up, already / spp ------ */
+/* ---- Film channel planes (src/film.rs:103-120), row-major, y up, already / spp ------
+ * Any plane pointer may be NULL: that channel is not written, like a Film<N> created without it
+ * (film.rs:175-203; add_sample ignores absent channels, film.rs:167-172).                  */
 typedef struct RaynFilmPlanes {
   float* color;      /* [3*W*H] Srgb                                                       */
   float* alpha;      /* [W*H]                                                              */
@@ -208,12 +219,8 @@ typedef struct RaynConfig {
 } RaynConfig;
 
 #define RAYN_FLAG_TIMING 1       /* record per-kernel CUDA-event times into RaynStats      */
-#define RAYN_FLAG_SIMPLE_MARCH 2 /* v0: one-thread-per-ray march kernels (no lane refill)  */
-#define RAYN_FLAG_BLOCK_POOL 4   /* v2: per-block refill / shadow pool instead of the default
-                                    pass-wide persistent march kernels                     */
-
-#define RAYN_FLAG_FLATTEN 8      /* experimental: iteration-granular march trips for the Mandelbulb
-                                    (measured slower than evaluation-granular trips; off by default) */
+#define RAYN_FLAG_SIMPLE_MARCH 2 /* TEST BUILD ONLY (-DRAYN_LEGACY_KERNELS, librayn_b200_legacy.so): round-1 v0
+                                    one-thread-per-ray kernels; RAYN_ERR_UNSUPPORTED in the product library */
 
 #define RAYN_STAT_KERNELS 12
 typedef struct RaynStats {
@@ -228,6 +235,10 @@ typedef struct RaynStats {
   float kernel_ms[RAYN_STAT_KERNELS];   /* RAYN_FLAG_TIMING: summed device ms per kernel   */
   int64_t kernel_launches[RAYN_STAT_KERNELS];
   float total_ms;                   /* device ms of the last render call (events)          */
+  int64_t sdf_evals_normals;        /* SDF dist() evaluations of get_shading_info (4 per SDF shading lane) */
+  int64_t bulb_iters_extend;        /* Mandelbulb iterations actually run inside K2 (data dependent)       */
+  int64_t bulb_iters_shadow;        /* ... inside K5                                                       */
+  int64_t reserved_;
 } RaynStats;
 
 /* indices into kernel_ms / kernel_launches */
@@ -240,13 +251,19 @@ enum {
   RAYN_K_SHADE_POST = 5,
   RAYN_K_COMPACT = 6,
   RAYN_K_RESOLVE = 7,
-  RAYN_K_MISC = 8
+  RAYN_K_MISC = 8,
+  RAYN_K_NORMALS = 9,
+  RAYN_K_EXTEND_SPHERES = 10,
+  RAYN_K_GATHER = 11
 };
 
 typedef struct RaynContext RaynContext;
 
 /* ---- lifecycle --------------------------------------------------------------------- */
 int32_t rayn_b200_abi_version(void);
+/* 1 if this library was built with `wide` f32x4::mul_add FUSED (rayn built with -C target-feature=+fma), 0 for the
+ * default: unfused, what a stock `cargo run --release` of the reference produces (oracle/README.md A6).          */
+int32_t rayn_b200_muladd_fused(void);
 int32_t rayn_b200_create(const RaynConfig* cfg, RaynContext** out_ctx);
 void rayn_b200_destroy(RaynContext* ctx);
 const char* rayn_b200_last_error(const RaynContext* ctx); /* ctx may be NULL: global slot */
@@ -262,9 +279,42 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* frame,
 
 int32_t rayn_b200_get_stats(const RaynContext* ctx, RaynStats* out);
 
-/* ---- multi-GPU film gather helpers (device pointers) --------------------------------
- * Tiles are disjoint (film.rs:82-98), so the gather MOVES bytes, it never reduces.
- * pack: copies the listed tiles out of full-size planes into a dense slab
+/* ---- multi-GPU: film tiles shard across GPUs, NCCL only for the final film gather -------------------------
+ * The reference's only parallelism is one rayon task per tile over shared read-only state (film.rs:640-649); the
+ * multi-GPU form of that is one context per GPU, each rendering the tiles `(tile_x + tile_y) % world == rank`
+ * (interleaved: fractal scenes are centre-weighted), and ONE all-gather of dense tile slabs at the end of the frame.
+ * The context owns the NCCL communicator (SURVEY §8b "Threading"):
+ *   one process per GPU : rank 0 calls comm_unique_id, the host distributes the 128 bytes by any means, every rank
+ *                         calls comm_init_rank on its context;
+ *   one process, n GPUs : comm_init_all(ctxs, n)  (ncclCommInitAll), then render_frame_multi.
+ * NCCL is dlopen()ed ("libnccl.so.2") at the first comm call: the library has no link-time NCCL dependency.      */
+#define RAYN_COMM_ID_BYTES 128
+int32_t rayn_b200_comm_unique_id(uint8_t out_id[RAYN_COMM_ID_BYTES]);
+int32_t rayn_b200_comm_init_rank(RaynContext* ctx, const uint8_t id[RAYN_COMM_ID_BYTES], int32_t rank, int32_t world);
+int32_t rayn_b200_comm_init_all(RaynContext* const* ctxs, int32_t n);
+int32_t rayn_b200_comm_destroy(RaynContext* ctx);
+int32_t rayn_b200_comm_info(const RaynContext* ctx, int32_t* rank, int32_t* world); /* world 0 = no communicator */
+/* the shard of `rank`: ascending tile indices with (tile_x + tile_y) % world == rank.  Returns the count (or the
+ * needed capacity if cap is too small / out is NULL); < 0 on bad arguments.  Pure host arithmetic.                */
+int32_t rayn_b200_shard_tiles(int32_t width, int32_t height, int32_t tile_w, int32_t tile_h, int32_t rank,
+                              int32_t world, int32_t* out, int32_t cap);
+/* render_frame for a context that holds a communicator: renders this rank's shard (frame->tile_list / tile_offset /
+ * tile_stride are ignored), then all-gathers, so EVERY rank ends with the complete film in `out`, bit-identical to
+ * the 1-GPU film.  Pack, ncclAllGather and unpack are enqueued on the render stream: no host synchronisation
+ * between render and gather.  DEVICE planes must be non-NULL for all four channels.                               */
+int32_t rayn_b200_render_frame_sharded(RaynContext* ctx, const RaynFrameDesc* frame, const RaynFilmPlanes* out);
+/* the gather alone, for planes already rendered with the rank's shard (device pointers, asynchronous on the context's
+ * stream; rayn_b200_sync waits).                                                                                  */
+int32_t rayn_b200_film_gather(RaynContext* ctx, int32_t width, int32_t height, int32_t tile_w, int32_t tile_h,
+                              const RaynFilmPlanes* planes_dev);
+int32_t rayn_b200_sync(RaynContext* ctx);
+/* one process driving n GPUs (contexts from comm_init_all, same scene uploaded to each): renders all shards
+ * concurrently, gathers, and returns the film of ctxs[0] in `out` (HOST planes).  frame inputs must be HOST pointers. */
+int32_t rayn_b200_render_frame_multi(RaynContext* const* ctxs, int32_t n, const RaynFrameDesc* frame,
+                                     const RaynFilmPlanes* out);
+
+/* ---- explicit slab helpers (device pointers): what the gather is made of; kept for hosts that bring their own
+ * transport.  pack: copies the listed tiles out of full-size planes into a dense slab
  *       [n_tiles][10][tile_w*tile_h] (channel order: color rgb, alpha, bg rgb, normal xyz)
  * unpack: scatters one rank's slab back into full-size planes.                           */
 int64_t rayn_b200_film_slab_floats(int32_t tile_w, int32_t tile_h, int32_t n_tiles);
@@ -317,6 +367,13 @@ int32_t rayn_b200_kat_detmath(RaynContext* ctx, int32_t op, int64_t n, const flo
 /* SDF::dist (sdf.rs:125-141) */
 int32_t rayn_b200_kat_sdf_dist(RaynContext* ctx, const RaynHitable* sdf, int64_t n,
                                const float* points3, float* out);
+/* the same through the packed two-point estimator the march kernels run (rt_sdf2.cuh); variant < 0 = the one the
+ * scheduler would pick for this hitable, else force 0 generic Mandelbox / 1 12-iteration fast / 2 n-iteration fast / 3 Mandelbulb */
+int32_t rayn_b200_kat_sdf_dist2(RaynContext* ctx, const RaynHitable* sdf, int32_t variant, int64_t n,
+                                const float* points3, float* out);
+/* Newton division of the Mandelbox sphere fold vs IEEE division: number of x among the n consecutive floats starting
+ * at bit pattern first_bits for which num / x differs (must be 0 wherever the fast variants are selected)           */
+int32_t rayn_b200_kat_fastdiv(RaynContext* ctx, float num, uint32_t first_bits, int64_t n, int64_t* out_mismatches);
 /* TracedSDF::hit (sdf.rs:59-83).  thr(t) = thr_scale * t, or thr_scale if thr_const != 0 */
 int32_t rayn_b200_kat_sdf_hit(RaynContext* ctx, const RaynHitable* sdf,
                               const RaynRenderConsts* consts, int64_t n, const float* origins3,

@@ -12,7 +12,8 @@ import numpy as np
 from rayn_b200 import _lib as L
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_build", "librayn_oracle.so")
+# the oracle variant always matches the product library's (rayn_b200/_lib.py): RAYN_MULADD_FUSED=1 -> `wide` mul_add fused (A6)
+LIB_PATH = os.path.join(HERE, "_build", "librayn_oracle_fma.so" if L.MULADD_FUSED else "librayn_oracle.so")
 fp = C.POINTER(C.c_float)
 _lib = None
 
@@ -20,7 +21,8 @@ _lib = None
 def build(force=False):
     src = os.path.join(HERE, "rayn_oracle.cpp")
     deps = [src, os.path.join(HERE, "..", "include", "rayn_b200.h"), os.path.join(HERE, "..", "rayn_b200", "csrc", "detmath.h")]
-    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps):
+    outs = [os.path.join(HERE, "_build", n) for n in ("librayn_oracle.so", "librayn_oracle_fma.so")]
+    if force or not all(os.path.exists(o) for o in outs) or any(os.path.getmtime(d) > min(os.path.getmtime(o) for o in outs) for d in deps):
         subprocess.run(["make", "-C", HERE, "-B"], check=True, capture_output=True)
     return LIB_PATH
 
@@ -48,6 +50,8 @@ def lib():
         l.rayn_oracle_film_postprocess.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(L.RaynFilmPlanes), C.c_void_p]
         if l.rayn_oracle_selfcheck() != 0:
             raise RuntimeError("oracle was built with FP contraction on: rebuild with -ffp-contract=off")
+        if l.rayn_oracle_muladd_fused() != (1 if L.MULADD_FUSED else 0):
+            raise RuntimeError("oracle library variant does not match RAYN_MULADD_FUSED")
         _lib = l
     return _lib
 
@@ -57,7 +61,7 @@ def _f(a):
 
 
 def render(world, camera, inputs, tile_size, integrator, time_range, n_threads=0, subsample_k=1, tile_offset=0, tile_stride=1,
-           queue_log=False):
+           queue_log=False, tile_list=None):
     """CPU render of the same FrameInputs.  Returns (planes dict, info dict)."""
     from rayn_b200.film import make_frame_desc
     desc, keep = world.flatten(camera)
@@ -68,7 +72,7 @@ def render(world, camera, inputs, tile_size, integrator, time_range, n_threads=0
                          planes["normal"].ctypes.data, L.MEM_HOST)
     ptrs = tuple(a.ctypes.data for a in inputs.arrays())
     f = make_frame_desc(w, h, tile_size, inputs.samples, integrator, inputs.frame, time_range, ptrs, L.MEM_HOST, tile_offset,
-                        tile_stride, (inputs.sets_1d, inputs.sets_2d))
+                        tile_stride, (inputs.sets_1d, inputs.sets_2d), tile_list)
     qbuf, qcap = None, 0
     if queue_log:
         qcap = 64 + 8 * (w * h * inputs.spp + 64 * 64) * (integrator.max_bounces + 1)

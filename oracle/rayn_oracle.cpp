@@ -82,7 +82,14 @@ inline F4 f4abs(F4 a) { return {_mm_andnot_ps(_mm_set1_ps(-0.0f), a.v)}; }
 inline F4 f4sqrt(F4 a) { return {_mm_sqrt_ps(a.v)}; }
 inline F4 f4min(F4 a, F4 b) { return {_mm_min_ps(a.v, b.v)}; }  // a.min(b): b if unordered
 inline F4 f4max(F4 a, F4 b) { return {_mm_max_ps(a.v, b.v)}; }  // a.max(b): b if unordered
-inline F4 mul_add(F4 a, F4 b, F4 c) { return {_mm_fmadd_ps(a.v, b.v, c.v)}; }  // a*b+c fused
+inline F4 fma4(F4 a, F4 b, F4 c) { return {_mm_fmadd_ps(a.v, b.v, c.v)}; }  // a*b+c fused: only where the arithmetic is ours (authored Mandelbulb)
+// wide 0.4.6 f32x4::mul_add (A6): `(self * b) + c` unless the crate is built with target_feature = "fma".
+// RAYN_MULADD_FUSED (detmath.h) selects; default 0 = what a stock `cargo run --release` of rayn produces.
+#if RAYN_MULADD_FUSED
+inline F4 mul_add(F4 a, F4 b, F4 c) { return {_mm_fmadd_ps(a.v, b.v, c.v)}; }
+#else
+inline F4 mul_add(F4 a, F4 b, F4 c) { return {_mm_add_ps(_mm_mul_ps(a.v, b.v), c.v)}; }
+#endif
 inline F4 cmp_lt(F4 a, F4 b) { return {_mm_cmplt_ps(a.v, b.v)}; }
 inline F4 cmp_le(F4 a, F4 b) { return {_mm_cmple_ps(a.v, b.v)}; }
 inline F4 cmp_gt(F4 a, F4 b) { return {_mm_cmpgt_ps(a.v, b.v)}; }
@@ -403,22 +410,22 @@ inline F4 mandelbulb_dist(const RaynHitable& h, V3 p) {
     F4 m2 = m * m, m3 = m2 * m;
     F4 r = f4sqrt(m);
     F4 r7 = m3 * r;
-    F4 ndr = mul_add(splat(8.0f) * r7, dr, one);
+    F4 ndr = fma4(splat(8.0f) * r7, dr, one);
     // polar part: a = z^2, b = r^2
     F4 a = w.z * w.z, b = m;
     F4 b2 = b * b, b3 = b2 * b, b4 = b2 * b2;
     // Horner forms with explicit fused multiply-adds (the definition is ours: DESIGN.md §7)
-    F4 P = mul_add(mul_add(mul_add(mul_add(splat(128.0f), a, splat(-256.0f) * b), a, splat(160.0f) * b2), a, splat(-32.0f) * b3), a, b4);
-    F4 A = mul_add(mul_add(mul_add(splat(128.0f), a, splat(-192.0f) * b), a, splat(80.0f) * b2), a, splat(-8.0f) * b3);
+    F4 P = fma4(fma4(fma4(fma4(splat(128.0f), a, splat(-256.0f) * b), a, splat(160.0f) * b2), a, splat(-32.0f) * b3), a, b4);
+    F4 A = fma4(fma4(fma4(splat(128.0f), a, splat(-192.0f) * b), a, splat(80.0f) * b2), a, splat(-8.0f) * b3);
     // azimuth part: a' = x^2, b' = rho^2
     F4 ax = w.x * w.x;
-    F4 q = mul_add(w.x, w.x, w.y * w.y);
+    F4 q = fma4(w.x, w.x, w.y * w.y);
     F4 q2 = q * q, q3 = q2 * q, q4 = q2 * q2;
-    F4 C = mul_add(mul_add(mul_add(mul_add(splat(128.0f), ax, splat(-256.0f) * q), ax, splat(160.0f) * q2), ax, splat(-32.0f) * q3), ax, q4);
-    F4 B = mul_add(mul_add(mul_add(splat(128.0f), ax, splat(-192.0f) * q), ax, splat(80.0f) * q2), ax, splat(-8.0f) * q3);
+    F4 C = fma4(fma4(fma4(fma4(splat(128.0f), ax, splat(-256.0f) * q), ax, splat(160.0f) * q2), ax, splat(-32.0f) * q3), ax, q4);
+    F4 B = fma4(fma4(fma4(splat(128.0f), ax, splat(-192.0f) * q), ax, splat(80.0f) * q2), ax, splat(-8.0f) * q3);
     F4 k = (w.z * A) / (q3 * f4sqrt(q));
     k = merge(cmp_gt(q, splat(0.0f)), k, splat(0.0f));
-    V3 nw = {mul_add(k, C, p.x), mul_add(k, w.x * w.y * B, p.y), P + p.z};
+    V3 nw = {fma4(k, C, p.x), fma4(k, w.x * w.y * B, p.y), P + p.z};
     F4 nm = dot(nw, nw);
     w = v3merge(esc, w, nw);
     dr = merge(esc, dr, ndr);
@@ -1088,6 +1095,7 @@ bool fp_contract_is_off() {
 extern "C" {
 
 int32_t rayn_oracle_selfcheck(void) { return fp_contract_is_off() ? 0 : 1; }
+int32_t rayn_oracle_muladd_fused(void) { return RAYN_MULADD_FUSED; }  // which A6 variant this library is (oracle/README.md)
 void rayn_oracle_set_decoupled_lights(int32_t on) { g_decoupled_lights = on; }  // TEST-ONLY, see g_decoupled_lights
 
 // Renders tiles with (tile_index % tile_stride) == tile_offset AND ((tile_index / tile_stride) % subsample_k) == 0.
@@ -1104,8 +1112,13 @@ int32_t rayn_oracle_render_frame(const RaynSceneDesc* scene, const RaynFrameDesc
   int stride = f->tile_stride > 0 ? f->tile_stride : 1;
   if (subsample_k < 1) subsample_k = 1;
   std::vector<int> todo;
-  for (int idx = 0; idx < ntx * nty; ++idx)
-    if (idx % stride == f->tile_offset && ((idx / stride) % subsample_k) == 0) todo.push_back(idx);
+  if (f->tile_list) {  // explicit tile set (same meaning as in rayn_b200_render_frame)
+    for (int i = 0; i < f->n_tile_list; ++i)
+      if (f->tile_list[i] >= 0 && f->tile_list[i] < ntx * nty) todo.push_back(f->tile_list[i]);
+  } else {
+    for (int idx = 0; idx < ntx * nty; ++idx)
+      if (idx % stride == f->tile_offset && ((idx / stride) % subsample_k) == 0) todo.push_back(idx);
+  }
   QueueLog ql{queue_log, queue_cap, 0};
   Counters total;
   if (queue_log) n_threads = 1;

@@ -8,7 +8,13 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "librayn_b200.so")
+# Which build of the library: RAYN_MULADD_FUSED=1 selects the variant with `wide` mul_add fused (oracle/README.md A6);
+# RAYN_B200_LEGACY=1 the TEST build that also carries the round-1 one-thread-per-ray kernels.  Default = the product.
+MULADD_FUSED = os.environ.get("RAYN_MULADD_FUSED", "0") == "1"
+LEGACY = os.environ.get("RAYN_B200_LEGACY", "0") == "1"
+LIB_NAME = "librayn_b200_fma.so" if MULADD_FUSED else ("librayn_b200_legacy.so" if LEGACY else "librayn_b200.so")
+LIB_PATH = os.path.join(_HERE, "_build", LIB_NAME)
+HOSTLIB_PATH = os.path.join(_HERE, "_build", "librayn_hostinputs.so")
 
 RAYN_MAX_HITABLES = 16
 RAYN_MAX_MATERIALS = 16
@@ -22,6 +28,8 @@ RAYN_ERR_CUDA = 3
 RAYN_ERR_OOM = 4
 RAYN_ERR_NO_SCENE = 5
 RAYN_ERR_NO_DEVICE = 6
+RAYN_ERR_NCCL = 7
+COMM_ID_BYTES = 128
 
 HITABLE_SPHERE, HITABLE_MANDELBOX, HITABLE_MANDELBULB = 0, 1, 2
 MATERIAL_LAMBERTIAN, MATERIAL_DIELECTRIC, MATERIAL_SKY, MATERIAL_EMISSIVE = 0, 1, 2, 3
@@ -29,9 +37,9 @@ CAMERA_PINHOLE, CAMERA_THINLENS, CAMERA_ORTHOGRAPHIC = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 POST_COLOR_PLUS_BACKGROUND, POST_COLOR_ALPHA, POST_COLOR_ONLY, POST_BACKGROUND, POST_WORLD_NORMAL, POST_ALPHA = range(6)
 POST_BYTES = (3, 4, 3, 3, 3, 1)
-FLAG_TIMING, FLAG_SIMPLE_MARCH, FLAG_BLOCK_POOL, FLAG_FLATTEN = 1, 2, 4, 8
+FLAG_TIMING, FLAG_SIMPLE_MARCH = 1, 2
 STAT_KERNELS = 12
-KERNEL_NAMES = ["raygen", "extend", "bin", "shade_pre", "shadow", "shade_post", "compact", "resolve", "misc"]
+KERNEL_NAMES = ["raygen", "extend", "bin", "shade_pre", "shadow", "shade_post", "compact", "resolve", "misc", "normals", "extend_spheres", "gather"]
 
 f32 = C.c_float
 i32 = C.c_int32
@@ -98,12 +106,26 @@ class RaynStats(C.Structure):
     _fields_ = [("launches", i64), ("passes", i64), ("paths", i64), ("extend_rays", i64),
                 ("shade_lanes", i64), ("shadow_rays", i64), ("sdf_evals_extend", i64),
                 ("sdf_evals_shadow", i64), ("kernel_ms", f32 * STAT_KERNELS),
-                ("kernel_launches", i64 * STAT_KERNELS), ("total_ms", f32)]
+                ("kernel_launches", i64 * STAT_KERNELS), ("total_ms", f32), ("sdf_evals_normals", i64),
+                ("bulb_iters_extend", i64), ("bulb_iters_shadow", i64), ("reserved_", i64)]
 
 
 # name -> (restype, argtypes); this table is also what the CPU test checks the header against
 SYMBOLS = {
     "rayn_b200_abi_version": (i32, []),
+    "rayn_b200_muladd_fused": (i32, []),
+    "rayn_b200_comm_unique_id": (i32, [C.c_void_p]),
+    "rayn_b200_comm_init_rank": (i32, [C.c_void_p, C.c_void_p, i32, i32]),
+    "rayn_b200_comm_init_all": (i32, [C.POINTER(C.c_void_p), i32]),
+    "rayn_b200_comm_destroy": (i32, [C.c_void_p]),
+    "rayn_b200_comm_info": (i32, [C.c_void_p, C.POINTER(i32), C.POINTER(i32)]),
+    "rayn_b200_shard_tiles": (i32, [i32, i32, i32, i32, i32, i32, C.POINTER(i32), i32]),
+    "rayn_b200_render_frame_sharded": (i32, [C.c_void_p, C.POINTER(RaynFrameDesc), C.POINTER(RaynFilmPlanes)]),
+    "rayn_b200_render_frame_multi": (i32, [C.POINTER(C.c_void_p), i32, C.POINTER(RaynFrameDesc), C.POINTER(RaynFilmPlanes)]),
+    "rayn_b200_film_gather": (i32, [C.c_void_p, i32, i32, i32, i32, C.POINTER(RaynFilmPlanes)]),
+    "rayn_b200_sync": (i32, [C.c_void_p]),
+    "rayn_b200_kat_sdf_dist2": (i32, [C.c_void_p, C.POINTER(RaynHitable), i32, i64, fp, fp]),
+    "rayn_b200_kat_fastdiv": (i32, [C.c_void_p, f32, C.c_uint32, i64, C.POINTER(i64)]),
     "rayn_b200_create": (i32, [C.POINTER(RaynConfig), C.POINTER(C.c_void_p)]),
     "rayn_b200_destroy": (None, [C.c_void_p]),
     "rayn_b200_last_error": (C.c_char_p, [C.c_void_p]),
@@ -131,7 +153,10 @@ SYMBOLS = {
     "rayn_b200_debug_read_queue_log": (i64, [C.c_void_p, C.POINTER(i32), i64]),
 }
 
+HOST_SYMBOLS = ("rayn_b200_host_rd_tables", "rayn_b200_host_scramble", "rayn_b200_host_fis_blackman_harris", "rayn_b200_host_tile_grid")
+
 _lib = None
+_hostlib = None
 
 
 class RaynError(RuntimeError):
@@ -157,7 +182,22 @@ def lib():
     return _lib
 
 
+def host_lib():
+    """The pure-CPU builders of the host-owned frame inputs (the rayn_b200_host_* entry points of the header), from
+    librayn_hostinputs.so: the same object code as in librayn_b200.so, without mapping the CUDA library."""
+    global _hostlib
+    if _hostlib is None:
+        if not os.path.exists(HOSTLIB_PATH):
+            raise ImportError(f"{HOSTLIB_PATH} is missing: build it with `python -m rayn_b200.build`")
+        l = C.CDLL(HOSTLIB_PATH)
+        for name in HOST_SYMBOLS:
+            fn = getattr(l, name)
+            fn.restype, fn.argtypes = SYMBOLS[name]
+        _hostlib = l
+    return _hostlib
+
+
 def check(code, ctx=None):
     if code != RAYN_OK:
-        msg = lib().rayn_b200_last_error(ctx)
+        msg = lib().rayn_b200_last_error(ctx) if (_lib is not None or ctx is not None) else None
         raise RaynError(code, msg.decode() if msg else "?")

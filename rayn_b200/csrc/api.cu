@@ -1,7 +1,9 @@
 // api.cu — C-ABI implementation (include/rayn_b200.h): context, scene upload, the tile-pass
-// scheduler that drives the wavefront kernels, film gather helpers and the known-answer
+// scheduler that drives the wavefront kernels, the NCCL film gather and the known-answer
 // entry points.  No torch types, no exceptions across the boundary.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <limits.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -11,6 +13,9 @@
 #include <vector>
 
 #include "rt_kernels.cuh"
+#ifdef RAYN_LEGACY_KERNELS
+#include "rt_legacy.cuh"
+#endif
 
 using namespace rt;
 
@@ -19,6 +24,34 @@ static thread_local std::string g_last_error;
 struct TimedLaunch {
   int kernel;
   cudaEvent_t a, b;
+};
+
+// ---- NCCL, resolved at run time (no link-time dependency: the library must load on a box without NCCL) ----
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[RAYN_COMM_ID_BYTES]; } ncclUniqueId;
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static const int kNcclFloat = 7;  // ncclFloat32
+
+struct RaynComm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 0;
+  // shard tables of the last geometry gathered
+  int W = 0, H = 0, tw = 0, th = 0, per_rank = 0;
+  std::vector<std::vector<int>> shards;
+  int* d_table = nullptr;   // [world * per_rank], -1 padded
+  float* d_slabs = nullptr; // [world * per_rank * 10 * tw * th]
+  size_t cap_slabs = 0;
 };
 
 struct RaynContext {
@@ -33,11 +66,13 @@ struct RaynContext {
   int64_t alloc_paths = 0, alloc_q = 0, alloc_seg = 0;
   int alloc_lc_ns = 0;
   int alloc_tiles = 0;
+  size_t pass_bytes = 0;
   PassBufs pb;
   int* d_tile_ids = nullptr;
   int* d_batch_prefix = nullptr;  // [alloc_tiles + 1]
-  int* d_work_ctr = nullptr;      // [4] global work counters of the persistent kernels
+  int* d_work_ctr = nullptr;      // [WC_TOTAL] global work counters of the persistent kernels
   int n_sm = 148;
+  int occ_ext[SDFV_COUNT], occ_shd[SDFV_COUNT];
   // staging for host-space inputs / outputs
   float *d_s1 = nullptr, *d_s2 = nullptr, *d_scr = nullptr, *d_fis = nullptr;
   size_t cap_s1 = 0, cap_s2 = 0, cap_scr = 0;
@@ -47,12 +82,19 @@ struct RaynContext {
   size_t cap_pack_ids = 0;
   unsigned char* d_post = nullptr;
   size_t cap_post = 0;
+  unsigned long long* d_kat = nullptr;
   RaynStats stats;
   bool qlog_enabled = false;
   std::vector<int32_t> qlog;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<TimedLaunch> timed;
   size_t timed_used = 0;
+  // a render that has been enqueued but not finished
+  bool pending = false;
+  std::vector<int> job_tiles;
+  int job_w = 0, job_h = 0, job_tw = 0, job_th = 0, job_spp = 0, job_nty = 0;
+  unsigned long long h_counters[CNT_TOTAL];
+  RaynComm comm;
 };
 
 static int32_t fail(RaynContext* ctx, int32_t code, const char* fmt, ...) {
@@ -65,12 +107,22 @@ static int32_t fail(RaynContext* ctx, int32_t code, const char* fmt, ...) {
   if (ctx) ctx->err = buf;
   return code;
 }
+// a failing runtime call leaves a sticky per-thread "last error": clear it when reporting, or the next valid call's
+// cudaGetLastError() check would fail spuriously
 #define CU(call)                                                                                     \
   do {                                                                                               \
     cudaError_t e_ = (call);                                                                         \
-    if (e_ != cudaSuccess)                                                                           \
+    if (e_ != cudaSuccess) {                                                                         \
+      cudaGetLastError();                                                                            \
       return fail(ctx, e_ == cudaErrorMemoryAllocation ? RAYN_ERR_OOM : RAYN_ERR_CUDA, "%s: %s (%s:%d)", #call, \
                   cudaGetErrorString(e_), __FILE__, __LINE__);                                       \
+    }                                                                                                \
+  } while (0)
+#define NC(call)                                                                                     \
+  do {                                                                                               \
+    int r_ = (call);                                                                                 \
+    if (r_ != 0)                                                                                     \
+      return fail(ctx, RAYN_ERR_NCCL, "%s: %s (%s:%d)", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?", __FILE__, __LINE__); \
   } while (0)
 
 template <class T>
@@ -91,7 +143,7 @@ static void free_pass(RaynContext* c) {
   cudaFree(c->d_tile_ids);
   cudaFree(c->d_batch_prefix);
   c->d_batch_prefix = nullptr;
-  cudaFree(p.nrm), cudaFree(p.vis), cudaFree(p.seg_a), cudaFree(p.seg_b), cudaFree(p.seg_owner), cudaFree(p.lc_c), cudaFree(p.lc_t);
+  cudaFree(p.nrm), cudaFree(p.vis), cudaFree(p.seg_a), cudaFree(p.seg_b), cudaFree(p.lc_c), cudaFree(p.lc_t);
   unsigned long long* counters = p.counters;
   memset(&p, 0, sizeof p);
   p.counters = counters;
@@ -99,46 +151,65 @@ static void free_pass(RaynContext* c) {
   c->alloc_paths = c->alloc_q = c->alloc_seg = 0;
   c->alloc_lc_ns = 0;
   c->alloc_tiles = 0;
+  c->pass_bytes = 0;
 }
 
-static int32_t ensure_pass(RaynContext* ctx, int n_tiles, int R, int QS, int seg_per_path, int lc_ns) {
+// bytes of pass state per path (what ensure_pass allocates), used to size passes against free device memory
+static size_t pass_bytes_per_path(int R, int QS, int seg_per_path, int lc_ns) {
+  return 6 * sizeof(float4) + 2 * sizeof(uint32_t) + 2 * sizeof(int) + (size_t)(((double)QS / R) * sizeof(int) + 1) + (size_t)lc_ns * sizeof(float4) +
+         (lc_ns > 4 ? 8 * sizeof(float) : 0) + (size_t)seg_per_path * 2 * sizeof(float4);
+}
+
+static int32_t ensure_pass(RaynContext* ctx, int n_tiles, int R, int QS, int seg_per_path_total, int n_sdf, int lc_ns) {
   const int64_t need_paths = (int64_t)n_tiles * R, need_q = (int64_t)n_tiles * QS;
-  const int64_t need_seg = need_paths * seg_per_path;
+  const int64_t need_seg = need_paths * seg_per_path_total;  // all SDF queues together
   if (need_paths <= ctx->alloc_paths && need_q <= ctx->alloc_q && n_tiles <= ctx->alloc_tiles && need_seg <= ctx->alloc_seg && lc_ns <= ctx->alloc_lc_ns)
     return RAYN_OK;
   free_pass(ctx);
   PassBufs& p = ctx->pb;
-  CU(cudaMalloc(&p.o_time, need_paths * sizeof(float4)));
-  CU(cudaMalloc(&p.d_t, need_paths * sizeof(float4)));
-  CU(cudaMalloc(&p.rad, need_paths * sizeof(float4)));
-  CU(cudaMalloc(&p.thr, need_paths * sizeof(float4)));
-  CU(cudaMalloc(&p.nrm0, need_paths * sizeof(float4)));
-  CU(cudaMalloc(&p.term, need_paths * sizeof(uint32_t)));
-  CU(cudaMalloc(&p.q_live, need_paths * sizeof(int)));
-  CU(cudaMalloc(&p.q_key, need_paths * sizeof(int)));
-  CU(cudaMalloc(&p.q_shade, need_q * sizeof(int)));
-  CU(cudaMalloc(&p.n_live, n_tiles * sizeof(int)));
-  CU(cudaMalloc(&p.n_slots, n_tiles * sizeof(int)));
-  CU(cudaMalloc(&p.bin_start, (size_t)n_tiles * (RAYN_MAX_HITABLES + 1) * sizeof(int)));
-  CU(cudaMalloc(&ctx->d_tile_ids, n_tiles * sizeof(int)));
-  CU(cudaMalloc(&ctx->d_batch_prefix, ((size_t)n_tiles + 1) * sizeof(int)));
-  CU(cudaMalloc(&p.nrm, need_paths * sizeof(float4)));
-  CU(cudaMalloc(&p.vis, need_paths * sizeof(uint32_t)));
+  size_t total = 0;
+#define PASS_ALLOC(ptr, bytes)                                    \
+  do {                                                            \
+    cudaError_t e_ = cudaMalloc((void**)&(ptr), (size_t)(bytes)); \
+    if (e_ != cudaSuccess) {                                      \
+      cudaGetLastError();                                         \
+      free_pass(ctx);                                             \
+      return fail(ctx, e_ == cudaErrorMemoryAllocation ? RAYN_ERR_OOM : RAYN_ERR_CUDA, "pass buffers (%lld paths): %s", (long long)need_paths, cudaGetErrorString(e_)); \
+    }                                                             \
+    total += (size_t)(bytes);                                     \
+  } while (0)
+  PASS_ALLOC(p.o_time, need_paths * sizeof(float4));
+  PASS_ALLOC(p.d_t, need_paths * sizeof(float4));
+  PASS_ALLOC(p.rad, need_paths * sizeof(float4));
+  PASS_ALLOC(p.thr, need_paths * sizeof(float4));
+  PASS_ALLOC(p.nrm0, need_paths * sizeof(float4));
+  PASS_ALLOC(p.term, need_paths * sizeof(uint32_t));
+  PASS_ALLOC(p.q_live, need_paths * sizeof(int));
+  PASS_ALLOC(p.q_key, need_paths * sizeof(int));
+  PASS_ALLOC(p.q_shade, need_q * sizeof(int));
+  PASS_ALLOC(p.n_live, n_tiles * sizeof(int));
+  PASS_ALLOC(p.n_slots, n_tiles * sizeof(int));
+  PASS_ALLOC(p.bin_start, (size_t)n_tiles * (RAYN_MAX_HITABLES + 1) * sizeof(int));
+  PASS_ALLOC(ctx->d_tile_ids, n_tiles * sizeof(int));
+  PASS_ALLOC(ctx->d_batch_prefix, ((size_t)n_tiles + 1) * sizeof(int));
+  PASS_ALLOC(p.nrm, need_paths * sizeof(float4));
+  PASS_ALLOC(p.vis, need_paths * sizeof(uint32_t));
   if (need_seg > 0) {
-    CU(cudaMalloc(&p.seg_a, need_seg * sizeof(float4)));
-    CU(cudaMalloc(&p.seg_b, need_seg * sizeof(float4)));
-    CU(cudaMalloc(&p.seg_owner, need_seg * sizeof(int)));
+    PASS_ALLOC(p.seg_a, need_seg * sizeof(float4));
+    PASS_ALLOC(p.seg_b, need_seg * sizeof(float4));
   }
-  p.seg_cap = need_seg;
+  p.seg_cap = n_sdf > 0 ? need_seg / n_sdf : 0;
   ctx->alloc_seg = need_seg;
   if (lc_ns > 0) {
-    CU(cudaMalloc(&p.lc_c, need_paths * lc_ns * sizeof(float4)));
-    if (lc_ns > 4) CU(cudaMalloc(&p.lc_t, need_paths * 8 * sizeof(float)));
+    PASS_ALLOC(p.lc_c, need_paths * lc_ns * sizeof(float4));
+    if (lc_ns > 4) PASS_ALLOC(p.lc_t, need_paths * 8 * sizeof(float));
   }
+#undef PASS_ALLOC
   ctx->alloc_lc_ns = lc_ns;
   ctx->alloc_paths = need_paths;
   ctx->alloc_q = need_q;
   ctx->alloc_tiles = n_tiles;
+  ctx->pass_bytes = total;
   return RAYN_OK;
 }
 
@@ -154,9 +225,9 @@ static void timed_begin(RaynContext* ctx, int kernel) {
   ctx->timed[ctx->timed_used].kernel = kernel;
   cudaEventRecord(ctx->timed[ctx->timed_used].a, ctx->stream);
 }
-static void timed_end(RaynContext* ctx, int kernel) {
-  ctx->stats.launches++;
-  ctx->stats.kernel_launches[kernel]++;
+static void timed_end(RaynContext* ctx, int kernel, int launches = 1) {
+  ctx->stats.launches += launches;
+  ctx->stats.kernel_launches[kernel] += launches;
   if (!(ctx->flags & RAYN_FLAG_TIMING)) return;
   cudaEventRecord(ctx->timed[ctx->timed_used].b, ctx->stream);
   ctx->timed_used++;
@@ -179,9 +250,38 @@ struct DevTmp {
   }
 };
 
+// kernel launches specialised on the SDF variant (rt_sdf2.cuh)
+#define DISPATCH_SDFV(v, STMT)                                                        \
+  switch (v) {                                                                        \
+    case SDFV_BOX_12_FAST: { constexpr int V = SDFV_BOX_12_FAST; STMT; } break;       \
+    case SDFV_BOX_N_FAST: { constexpr int V = SDFV_BOX_N_FAST; STMT; } break;         \
+    case SDFV_BULB: { constexpr int V = SDFV_BULB; STMT; } break;                     \
+    default: { constexpr int V = SDFV_BOX_GENERIC; STMT; } break;                     \
+  }
+
+static void tile_grid_of(int W, int H, int tw, int th, int* ntx, int* nty) {
+  *ntx = (W + W % tw) / tw;  // film.rs:399-404
+  *nty = (H + H % th) / th;
+}
+static std::vector<int> shard_of(int W, int H, int tw, int th, int rank, int world) {
+  int ntx, nty;
+  tile_grid_of(W, H, tw, th, &ntx, &nty);
+  std::vector<int> v;
+  for (int tx = 0; tx < ntx; ++tx)
+    for (int ty = 0; ty < nty; ++ty)
+      if ((tx + ty) % world == rank) v.push_back(tx * nty + ty);  // ascending: tile index = tx * nty + ty (film.rs:401-425)
+  return v;
+}
+
+static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const RaynFilmPlanes* out, const std::vector<int>* tiles_override,
+                              RaynFilmPlanes* dev_planes_out);
+static int32_t render_finish(RaynContext* ctx);
+static int32_t gather_enqueue(RaynContext* ctx, int W, int H, int tw, int th, const RaynFilmPlanes* pl, bool in_group);
+
 extern "C" {
 
 int32_t rayn_b200_abi_version(void) { return RAYN_B200_ABI_VERSION; }
+int32_t rayn_b200_muladd_fused(void) { return RAYN_MULADD_FUSED; }
 
 const char* rayn_b200_last_error(const RaynContext* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
 
@@ -196,23 +296,38 @@ int32_t rayn_b200_create(const RaynConfig* cfg, RaynContext** out_ctx) {
   }
   const int dev = cfg ? cfg->device : 0;
   if (dev < 0 || dev >= ndev) return fail(nullptr, RAYN_ERR_INVALID_ARG, "device %d out of range (have %d)", dev, ndev);
+#ifndef RAYN_LEGACY_KERNELS
+  if (cfg && (cfg->flags & RAYN_FLAG_SIMPLE_MARCH))
+    return fail(nullptr, RAYN_ERR_UNSUPPORTED, "RAYN_FLAG_SIMPLE_MARCH needs the test build (librayn_b200_legacy.so, -DRAYN_LEGACY_KERNELS)");
+#endif
   CU(cudaSetDevice(dev));
   ctx = new RaynContext();
   ctx->device = dev;
   ctx->flags = cfg ? cfg->flags : 0;
-  ctx->cap_paths = (cfg && cfg->max_paths_per_pass > 0) ? cfg->max_paths_per_pass : (int64_t)96 << 20;  // ~25 GB of path state + shadow queue; fewer passes = fewer kernel tails (measured +3.5 %)
+  ctx->cap_paths = (cfg && cfg->max_paths_per_pass > 0) ? cfg->max_paths_per_pass : (int64_t)96 << 20;  // fewer passes = fewer kernel tails (measured +3.5 %); clamped to free memory per frame
   memset(&ctx->pb, 0, sizeof ctx->pb);
   memset(&ctx->stats, 0, sizeof ctx->stats);
   memset(&ctx->scene, 0, sizeof ctx->scene);
   cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaMalloc(&ctx->pb.counters, 8 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->pb.counters, CNT_TOTAL * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&ctx->d_fis, RAYN_FIS_TABLE_SIZE * sizeof(float));
-  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_work_ctr, 4 * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_work_ctr, WC_TOTAL * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&ctx->d_kat, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, dev);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+  // persistent kernels: exactly as many CTAs as can be resident (one wave), so every CTA pulls work until the pass is drained
+  for (int v = 0; v < SDFV_COUNT && e == cudaSuccess; ++v) {
+    DISPATCH_SDFV(v, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_ext[v], k_extend_march<V>, EXT_T, 0);
+                  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shd[v], k_shadow<V>, SHD_T, 0));
+  }
   if (e != cudaSuccess) {
+    cudaGetLastError();
     fail(nullptr, RAYN_ERR_CUDA, "context setup: %s", cudaGetErrorString(e));
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    cudaFree(ctx->pb.counters), cudaFree(ctx->d_fis), cudaFree(ctx->d_work_ctr), cudaFree(ctx->d_kat);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     delete ctx;
     return RAYN_ERR_CUDA;
   }
@@ -220,13 +335,26 @@ int32_t rayn_b200_create(const RaynConfig* cfg, RaynContext** out_ctx) {
   return RAYN_OK;
 }
 
+int32_t rayn_b200_comm_destroy(RaynContext* ctx) {
+  if (!ctx) return RAYN_ERR_INVALID_ARG;
+  RaynComm& c = ctx->comm;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (c.comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c.comm);
+  cudaFree(c.d_table), cudaFree(c.d_slabs);
+  c = RaynComm();
+  return RAYN_OK;
+}
+
 void rayn_b200_destroy(RaynContext* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  rayn_b200_comm_destroy(ctx);
   free_pass(ctx);
   cudaFree(ctx->pb.counters);
   cudaFree(ctx->d_work_ctr);
+  cudaFree(ctx->d_kat);
   cudaFree(ctx->d_pack_ids);
   cudaFree(ctx->d_post);
   cudaFree(ctx->d_s1), cudaFree(ctx->d_s2), cudaFree(ctx->d_scr), cudaFree(ctx->d_fis), cudaFree(ctx->d_planes);
@@ -272,6 +400,7 @@ int32_t rayn_b200_upload_scene(RaynContext* ctx, const RaynSceneDesc* s) {
   d.n_hit = s->n_hitables;
   d.n_mat = s->n_materials;
   d.n_lights = s->n_lights;
+  d.one = 1.0f;
   memcpy(d.hit, s->hitables, sizeof(RaynHitable) * s->n_hitables);
   memcpy(d.mat, s->materials, sizeof(RaynMaterial) * s->n_materials);
   if (s->n_lights) memcpy(d.light, s->lights, sizeof(RaynLight) * s->n_lights);
@@ -301,8 +430,15 @@ int64_t rayn_b200_debug_read_queue_log(RaynContext* ctx, int32_t* out, int64_t c
   return n;
 }
 
-int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const RaynFilmPlanes* out) {
+}  // extern "C"
+
+// Enqueues one render on the context's stream.  Nothing here waits for the GPU (except the debug queue log), so a single
+// host thread can keep several GPUs busy (render_frame_multi).  tiles_override replaces the frame's own tile selection.
+// dev_planes_out (optional) receives the device-space planes the film was rendered into.
+static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const RaynFilmPlanes* out, const std::vector<int>* tiles_override,
+                              RaynFilmPlanes* dev_planes_out) {
   if (!ctx) return fail(nullptr, RAYN_ERR_INVALID_ARG, "ctx is NULL");
+  if (ctx->pending) return fail(ctx, RAYN_ERR_INVALID_ARG, "a render is already in flight on this context");
   if (!ctx->has_scene) return fail(ctx, RAYN_ERR_NO_SCENE, "render_frame before upload_scene");
   if (!f || !out) return fail(ctx, RAYN_ERR_INVALID_ARG, "frame/out is NULL");
   if (f->width <= 0 || f->height <= 0 || f->tile_w <= 0 || f->tile_h <= 0 || f->samples <= 0 || f->max_bounces < 0)
@@ -314,27 +450,33 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
   if (f->sets_1d < need1 || f->sets_2d < need2)
     return fail(ctx, RAYN_ERR_INVALID_ARG, "sample tables too small: have %d/%d sets, path needs %d/%d", f->sets_1d, f->sets_2d, need1, need2);
   if (!f->samples_1d || !f->samples_2d || !f->scramble || !f->fis_inverse_cdf) return fail(ctx, RAYN_ERR_INVALID_ARG, "NULL input table");
-  if (!out->color || !out->alpha || !out->background || !out->normal) return fail(ctx, RAYN_ERR_INVALID_ARG, "NULL film plane");
   const int stride = f->tile_stride > 0 ? f->tile_stride : 1;
-  if (f->tile_offset < 0 || f->tile_offset >= stride) return fail(ctx, RAYN_ERR_INVALID_ARG, "tile_offset %d not in [0,%d)", f->tile_offset, stride);
-  if (mb > 1022) return fail(ctx, RAYN_ERR_UNSUPPORTED, "max_bounces > 1022");
+  if (!tiles_override && !f->tile_list && (f->tile_offset < 0 || f->tile_offset >= stride))
+    return fail(ctx, RAYN_ERR_INVALID_ARG, "tile_offset %d not in [0,%d)", f->tile_offset, stride);
+  if (mb >= TERM_MAX_DEPTH) return fail(ctx, RAYN_ERR_UNSUPPORTED, "max_bounces > %d", TERM_MAX_DEPTH - 1);
   const int64_t R64 = (int64_t)f->tile_w * f->tile_h * spp;
   const int n_hit = ctx->scene.n_hit;
-  if (R64 + 4 * n_hit >= (1 << 20))
-    return fail(ctx, RAYN_ERR_UNSUPPORTED, "tile_w*tile_h*spp = %lld exceeds the 2^20 slot key space", (long long)R64);
+  if (R64 + 4 * n_hit >= TERM_MAX_SLOTS)
+    return fail(ctx, RAYN_ERR_UNSUPPORTED, "tile_w*tile_h*spp = %lld exceeds the 2^%d slot key space", (long long)R64, TERM_DEPTH_SHIFT);
+  int np = 32;
+  while (np < spp) np <<= 1;
+  const int wpc = resolve_warps_per_cta(np);
+  if (wpc < 1 || np > 65536) return fail(ctx, RAYN_ERR_UNSUPPORTED, "spp = %d: the film resolve holds 12 B per sample of a pixel in shared memory (max 16384 spp)", spp);
   const int R = (int)R64, QS = R + 4 * n_hit;
   CU(cudaSetDevice(ctx->device));
 
   DevFrame fr;
   fr.W = f->width, fr.H = f->height, fr.tile_w = f->tile_w, fr.tile_h = f->tile_h;
   fr.samples = f->samples, fr.spp = spp, fr.max_bounces = mb, fr.vm = vm;
-  fr.ntx = (f->width + f->width % f->tile_w) / f->tile_w;      // film.rs:399-404
-  fr.nty = (f->height + f->height % f->tile_h) / f->tile_h;
+  tile_grid_of(f->width, f->height, f->tile_w, f->tile_h, &fr.ntx, &fr.nty);
   fr.sets_1d = f->sets_1d, fr.sets_2d = f->sets_2d;
   fr.t0 = f->t0, fr.t1 = f->t1;
 
-  std::vector<int> my_tiles;
-  if (f->tile_list) {
+  std::vector<int>& my_tiles = ctx->job_tiles;
+  my_tiles.clear();
+  if (tiles_override) {
+    my_tiles = *tiles_override;
+  } else if (f->tile_list) {
     if (f->n_tile_list < 0) return fail(ctx, RAYN_ERR_INVALID_ARG, "n_tile_list < 0");
     for (int i = 0; i < f->n_tile_list; ++i) {
       const int idx = f->tile_list[i];
@@ -375,46 +517,52 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
     p_color = ctx->d_planes, p_alpha = p_color + 3 * npx, p_bg = p_alpha + npx, p_normal = p_bg + 3 * npx;
   } else {
     p_color = out->color, p_alpha = out->alpha, p_bg = out->background, p_normal = out->normal;
+    const int cov_w = std::min(fr.ntx * f->tile_w, f->width), cov_h = std::min(fr.nty * f->tile_h, f->height);
+    if (cov_w < f->width || cov_h < f->height)
+      k_zero_uncovered<<<(unsigned)((npx + 255) / 256), 256, 0, st>>>(f->width, f->height, cov_w, cov_h, p_color, p_alpha, p_bg, p_normal);
+  }
+  if (dev_planes_out) {
+    dev_planes_out->color = p_color, dev_planes_out->alpha = p_alpha, dev_planes_out->background = p_bg, dev_planes_out->normal = p_normal;
+    dev_planes_out->space = RAYN_MEM_DEVICE;
   }
 
-  int tiles_per_pass = (int)std::max<int64_t>(1, ctx->cap_paths / R);
-  tiles_per_pass = std::min(tiles_per_pass, 65535);
-  tiles_per_pass = std::min<int>(tiles_per_pass, std::max<size_t>(my_tiles.size(), 1));
   int n_sdf = 0;
-  for (int i = 0; i < n_hit; ++i) n_sdf += ctx->scene.hit[i].kind != RAYN_HITABLE_SPHERE;
-  // kernel family: v3 (default) pass-wide persistent march kernels; v2 per-block pools; v0 one thread per ray
+  int sdf_idx[RAYN_MAX_HITABLES];
+  for (int i = 0; i < n_hit; ++i)
+    if (ctx->scene.hit[i].kind != RAYN_HITABLE_SPHERE) sdf_idx[n_sdf++] = i;
   const bool simple = (ctx->flags & RAYN_FLAG_SIMPLE_MARCH) != 0;
-  const bool block_pool = !simple && (ctx->flags & RAYN_FLAG_BLOCK_POOL) != 0 && n_sdf <= SH_MAX_SDF;
-  const bool v3 = !simple && !block_pool;
-  bool motion = false;  // time-varying sphere centres need the packet's lane-0 time: only the default kernel family plumbs it
+  bool motion = false;  // time-varying sphere centres need the packet's lane-0 time: only the product kernels plumb it
   for (int i = 0; i < n_hit; ++i)
     motion |= ctx->scene.hit[i].kind == RAYN_HITABLE_SPHERE && (ctx->scene.hit[i].center_velocity[0] != 0.0f || ctx->scene.hit[i].center_velocity[1] != 0.0f ||
                                                                  ctx->scene.hit[i].center_velocity[2] != 0.0f);
-  if (motion && !v3) return fail(ctx, RAYN_ERR_UNSUPPORTED, "time-varying sphere centres are only supported by the default kernel family (no RAYN_FLAG_SIMPLE_MARCH / BLOCK_POOL)");
-  const bool no_flat = (ctx->flags & RAYN_FLAG_FLATTEN) == 0;
-  // persistent kernels: exactly as many CTAs as can be resident (one wave), so every CTA pulls work until the pass is drained
-  int occ_ext = 8, occ_ext_flat = 8, occ_shd = 8, occ_shd_flat = 8;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ext, k_extend_march<false>, EXT_T, 0));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_ext_flat, k_extend_march<true>, EXT_T, 0));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_shd, k_shadow<false>, SHD_T, 0));
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_shd_flat, k_shadow<true>, SHD_T, 0));
-  bool any_bulb = false;
-  for (int i = 0; i < n_hit; ++i) any_bulb |= ctx->scene.hit[i].kind == RAYN_HITABLE_MANDELBULB;
+  if (motion && simple) return fail(ctx, RAYN_ERR_UNSUPPORTED, "time-varying sphere centres are not supported by the legacy test kernels");
   const bool volume_on = ctx->scene.vol.has_scattering != 0 && ctx->scene.n_lights > 0;
-  const int seg_per_path = v3 ? (volume_on ? 4 * (1 + vm) : 4) * n_sdf : 0;  // worst case shadow segments per path per depth
-  if (v3 && volume_on) tiles_per_pass = std::max(1, tiles_per_pass / 3);
-  const int lc_ns = v3 ? (volume_on ? 4 * (1 + vm) : 4) : 0;  // stored light contributions per path per depth
-  int32_t rc = ensure_pass(ctx, tiles_per_pass, R, QS, seg_per_path, lc_ns);
+  const int ns = volume_on ? 4 * (1 + vm) : 4;               // light samples per path per depth
+  const int seg_per_path = simple ? 0 : ns * n_sdf;          // worst case shadow segments per path per depth, all SDF queues
+  const int lc_ns = simple ? 0 : ns;                         // stored light contributions per path per depth
+
+  // pass size: as many tiles as the requested path budget AND free device memory allow
+  const size_t bpp = pass_bytes_per_path(R, QS, seg_per_path, lc_ns);
+  size_t free_b = 0, total_b = 0;
+  CU(cudaMemGetInfo(&free_b, &total_b));
+  const size_t budget = (size_t)((double)(free_b + ctx->pass_bytes) * 0.90);
+  int64_t max_paths = std::min<int64_t>(ctx->cap_paths, (int64_t)(budget / bpp));
+  if (n_sdf > 0) max_paths = std::min<int64_t>(max_paths, ((int64_t)1 << 27) - 1);          // owner path index is packed with the sample bit (<< 4)
+  if (n_sdf > 0) max_paths = std::min<int64_t>(max_paths, (int64_t)INT_MAX / std::max(ns, 1));  // 32-bit queue cursors per SDF
+  int tiles_per_pass = (int)std::max<int64_t>(1, max_paths / R);
+  tiles_per_pass = std::min(tiles_per_pass, 65535);
+  tiles_per_pass = std::min<int>(tiles_per_pass, (int)std::max<size_t>(my_tiles.size(), 1));
+  int32_t rc;
+  while ((rc = ensure_pass(ctx, tiles_per_pass, R, QS, seg_per_path, n_sdf, lc_ns)) == RAYN_ERR_OOM && tiles_per_pass > 1)
+    tiles_per_pass = (tiles_per_pass + 1) / 2;  // fragmentation / another tenant: retry with half the pass
   if (rc) return rc;
   PassBufs pb = ctx->pb;
   pb.R = R, pb.QS = QS, pb.tile_ids = ctx->d_tile_ids;
   pb.lc_ns = lc_ns;
-  pb.seg_count = ctx->d_work_ctr + 2;
-  CU(cudaMemsetAsync(pb.counters, 0, 8 * sizeof(unsigned long long), st));
-  int np = 2;
-  while (np < spp) np <<= 1;
-  CU(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)resolve_smem_bytes(np)));
-  if (block_pool) CU(cudaFuncSetAttribute(k_shade2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shade_smem_bytes(n_sdf)));
+  pb.seg_count = ctx->d_work_ctr + WC_SEG_COUNT;
+  CU(cudaMemsetAsync(pb.counters, 0, CNT_TOTAL * sizeof(unsigned long long), st));
+  const size_t res_smem = resolve_smem_per_warp(np) * wpc;
+  CU(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem));
 
   std::vector<int> h_nslots, h_slots;
   for (size_t first = 0; first < my_tiles.size(); first += tiles_per_pass) {
@@ -422,45 +570,44 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
     pb.n_tiles = nt;
     CU(cudaMemcpyAsync(ctx->d_tile_ids, my_tiles.data() + first, nt * sizeof(int), cudaMemcpyHostToDevice, st));
     ctx->stats.passes++;
-    const dim3 g_paths((R + 255) / 256, nt), g_ext((R + 127) / 128, nt), g_shade((QS + 127) / 128, nt);
+    const dim3 g_paths((R + 255) / 256, nt), g_shade((QS + 127) / 128, nt);
     timed_begin(ctx, RAYN_K_RAYGEN);
     k_raygen<<<g_paths, 256, 0, st>>>(ctx->scene, fr, pb);
     timed_end(ctx, RAYN_K_RAYGEN);
     for (int depth = 0; depth <= mb; ++depth) {
       const Thr thr = make_thr(ctx->scene.cam, depth);
-      timed_begin(ctx, RAYN_K_EXTEND);
       if (simple) {
-        k_extend<<<g_ext, 128, 0, st>>>(ctx->scene, pb, thr);
-      } else if (block_pool) {
-        k_extend2<<<dim3((R + EXT_CHUNK - 1) / EXT_CHUNK, nt), EXT_T, 0, st>>>(ctx->scene, pb, thr);
+#ifdef RAYN_LEGACY_KERNELS
+        timed_begin(ctx, RAYN_K_EXTEND);
+        k_extend<<<dim3((R + 127) / 128, nt), 128, 0, st>>>(ctx->scene, pb, thr);
+        timed_end(ctx, RAYN_K_EXTEND);
+#endif
       } else {
+        timed_begin(ctx, RAYN_K_MISC);
         k_scan_live<<<1, SCAN_T, 0, st>>>(pb, ctx->d_batch_prefix, ctx->d_work_ctr);
-        ctx->stats.launches++;
-        ctx->stats.kernel_launches[RAYN_K_MISC]++;
+        timed_end(ctx, RAYN_K_MISC);
         // fold order of hitable.rs:177-198: runs of spheres as coherent kernels, each SDF as a persistent march
         int k = 0, first_kernel = 1, n_march = 0;
         while (k < n_hit || first_kernel) {
           int e = k;
           while (e < n_hit && ctx->scene.hit[e].kind == RAYN_HITABLE_SPHERE) ++e;
           if (e > k || first_kernel) {
+            timed_begin(ctx, RAYN_K_EXTEND_SPHERES);
             k_extend_spheres<<<g_paths, 256, 0, st>>>(ctx->scene, pb, k, e, first_kernel, motion ? 1 : 0);
-            ctx->stats.launches++;
+            timed_end(ctx, RAYN_K_EXTEND_SPHERES);
             first_kernel = 0;
           }
           if (e < n_hit) {
-            if (n_march++ > 0) CU(cudaMemsetAsync(ctx->d_work_ctr, 0, sizeof(int), st));
-            if (ctx->scene.hit[e].kind == RAYN_HITABLE_MANDELBULB && !no_flat)
-              k_extend_march<true><<<ctx->n_sm * occ_ext_flat, EXT_T, 0, st>>>(ctx->scene, pb, thr, e, ctx->d_batch_prefix, ctx->d_work_ctr);
-            else
-              k_extend_march<false><<<ctx->n_sm * occ_ext, EXT_T, 0, st>>>(ctx->scene, pb, thr, e, ctx->d_batch_prefix, ctx->d_work_ctr);
-            ctx->stats.launches++;
+            if (n_march++ > 0) CU(cudaMemsetAsync(ctx->d_work_ctr + WC_EXTEND, 0, sizeof(int), st));
+            const int v = sdf_variant(ctx->scene.hit[e]);
+            timed_begin(ctx, RAYN_K_EXTEND);
+            DISPATCH_SDFV(v, (k_extend_march<V><<<ctx->n_sm * ctx->occ_ext[v], EXT_T, 0, st>>>(ctx->scene, pb, thr, e, ctx->d_batch_prefix, ctx->d_work_ctr + WC_EXTEND)));
+            timed_end(ctx, RAYN_K_EXTEND);
             ++e;
           }
           k = e;
         }
-        ctx->stats.launches--;  // timed_end below counts one launch of this group
       }
-      timed_end(ctx, RAYN_K_EXTEND);
       timed_begin(ctx, RAYN_K_BIN);
       k_bin<<<nt, BIN_T, 0, st>>>(pb, n_hit);
       timed_end(ctx, RAYN_K_BIN);
@@ -477,28 +624,37 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
           for (int s = 0; s < h_nslots[t]; ++s) ctx->qlog.push_back(h_slots[(size_t)t * QS + s]);
         }
       }
-      if (v3) {
+      if (!simple) {
+        // get_shading_info of the SDF hitables whose material is shaded (receives light, or volumetrics sample along the ray)
+        for (int j = 0; j < n_sdf; ++j) {
+          const RaynHitable& h = ctx->scene.hit[sdf_idx[j]];
+          const int mk = ctx->scene.mat[h.material].kind;
+          if (!(mk == RAYN_MATERIAL_LAMBERTIAN || mk == RAYN_MATERIAL_DIELECTRIC || volume_on)) continue;
+          const int v = sdf_variant(h);
+          timed_begin(ctx, RAYN_K_NORMALS);
+          DISPATCH_SDFV(v, (k_normals<V><<<g_shade, 128, 0, st>>>(ctx->scene, pb, thr, sdf_idx[j])));
+          timed_end(ctx, RAYN_K_NORMALS);
+        }
         timed_begin(ctx, RAYN_K_SHADE_PRE);
         k_shade_pre<<<g_shade, 128, 0, st>>>(ctx->scene, fr, pb, depth, thr);
         timed_end(ctx, RAYN_K_SHADE_PRE);
-        if (n_sdf > 0 && ctx->scene.n_lights > 0) {
-          timed_begin(ctx, RAYN_K_SHADOW);
-          if (any_bulb && !no_flat)
-            k_shadow<true><<<ctx->n_sm * occ_shd_flat, SHD_T, 0, st>>>(ctx->scene, pb, ctx->d_work_ctr + 1);
-          else
-            k_shadow<false><<<ctx->n_sm * occ_shd, SHD_T, 0, st>>>(ctx->scene, pb, ctx->d_work_ctr + 1);
-          timed_end(ctx, RAYN_K_SHADOW);
+        if (ctx->scene.n_lights > 0) {
+          for (int j = 0; j < n_sdf; ++j) {
+            const int v = sdf_variant(ctx->scene.hit[sdf_idx[j]]);
+            timed_begin(ctx, RAYN_K_SHADOW);
+            DISPATCH_SDFV(v, (k_shadow<V><<<ctx->n_sm * ctx->occ_shd[v], SHD_T, 0, st>>>(ctx->scene, pb, sdf_idx[j], j, ctx->d_work_ctr + WC_SHADOW + j)));
+            timed_end(ctx, RAYN_K_SHADOW);
+          }
         }
         timed_begin(ctx, RAYN_K_SHADE_POST);
         k_shade_post<<<g_shade, 128, 0, st>>>(ctx->scene, fr, pb, depth);
         timed_end(ctx, RAYN_K_SHADE_POST);
       } else {
+#ifdef RAYN_LEGACY_KERNELS
         timed_begin(ctx, RAYN_K_SHADE_PRE);
-        if (simple)
-          k_shade<<<g_shade, 128, 0, st>>>(ctx->scene, fr, pb, depth, thr);
-        else
-          k_shade2<<<dim3((QS + SH_T - 1) / SH_T, nt), SH_T, shade_smem_bytes(n_sdf), st>>>(ctx->scene, fr, pb, depth, thr, SH_POOL * std::max(n_sdf, 1));
+        k_shade<<<g_shade, 128, 0, st>>>(ctx->scene, fr, pb, depth, thr);
         timed_end(ctx, RAYN_K_SHADE_PRE);
+#endif
       }
       if (depth < mb) {
         timed_begin(ctx, RAYN_K_COMPACT);
@@ -507,34 +663,54 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
       }
     }
     timed_begin(ctx, RAYN_K_RESOLVE);
-    k_resolve<<<dim3(f->tile_w * f->tile_h, nt), RES_T, resolve_smem_bytes(np), st>>>(fr, pb, p_color, p_alpha, p_bg, p_normal, np);
+    k_resolve<<<dim3((f->tile_w * f->tile_h + wpc - 1) / wpc, nt), wpc * 32, res_smem, st>>>(fr, pb, p_color, p_alpha, p_bg, p_normal, np, wpc);
     timed_end(ctx, RAYN_K_RESOLVE);
     CU(cudaGetLastError());
   }
-  if (out->space == RAYN_MEM_HOST) {
-    CU(cudaMemcpyAsync(out->color, p_color, npx * 3 * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(out->alpha, p_alpha, npx * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(out->background, p_bg, npx * 3 * 4, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(out->normal, p_normal, npx * 3 * 4, cudaMemcpyDeviceToHost, st));
-  }
+  ctx->job_w = f->width, ctx->job_h = f->height, ctx->job_tw = f->tile_w, ctx->job_th = f->tile_h, ctx->job_spp = spp, ctx->job_nty = fr.nty;
+  ctx->pending = true;
+  return RAYN_OK;
+}
+
+// D2H of host-space planes (after an optional gather), then the end-of-frame bookkeeping
+static int32_t copy_out_enqueue(RaynContext* ctx, const RaynFilmPlanes* out) {
+  if (out->space != RAYN_MEM_HOST) return RAYN_OK;
+  cudaStream_t st = ctx->stream;
+  const size_t npx = (size_t)ctx->job_w * ctx->job_h;
+  const float* d = ctx->d_planes;
+  if (out->color) CU(cudaMemcpyAsync(out->color, d, npx * 3 * 4, cudaMemcpyDeviceToHost, st));
+  if (out->alpha) CU(cudaMemcpyAsync(out->alpha, d + 3 * npx, npx * 4, cudaMemcpyDeviceToHost, st));
+  if (out->background) CU(cudaMemcpyAsync(out->background, d + 4 * npx, npx * 3 * 4, cudaMemcpyDeviceToHost, st));
+  if (out->normal) CU(cudaMemcpyAsync(out->normal, d + 7 * npx, npx * 3 * 4, cudaMemcpyDeviceToHost, st));
+  return RAYN_OK;
+}
+
+static int32_t render_finish(RaynContext* ctx) {
+  if (!ctx->pending) return RAYN_OK;
+  ctx->pending = false;
+  cudaStream_t st = ctx->stream;
+  CU(cudaSetDevice(ctx->device));
   CU(cudaEventRecord(ctx->ev1, st));
-  unsigned long long h_counters[8];
-  CU(cudaMemcpyAsync(h_counters, pb.counters, sizeof h_counters, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(ctx->h_counters, ctx->pb.counters, sizeof ctx->h_counters, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   CU(cudaGetLastError());
   CU(cudaEventElapsedTime(&ctx->stats.total_ms, ctx->ev0, ctx->ev1));
-  ctx->stats.extend_rays = (int64_t)h_counters[CNT_EXTEND_RAYS];
-  ctx->stats.shade_lanes = (int64_t)h_counters[CNT_SHADE_LANES];
-  ctx->stats.shadow_rays = (int64_t)h_counters[CNT_SHADOW_RAYS];
-  ctx->stats.sdf_evals_extend = (int64_t)h_counters[CNT_EVALS_EXTEND];
-  ctx->stats.sdf_evals_shadow = (int64_t)h_counters[CNT_EVALS_SHADOW];
+  const unsigned long long* h = ctx->h_counters;
+  ctx->stats.extend_rays = (int64_t)h[CNT_EXTEND_RAYS];
+  ctx->stats.shade_lanes = (int64_t)h[CNT_SHADE_LANES];
+  ctx->stats.shadow_rays = (int64_t)h[CNT_SHADOW_RAYS];
+  ctx->stats.sdf_evals_extend = (int64_t)h[CNT_EVALS_EXTEND];
+  ctx->stats.sdf_evals_shadow = (int64_t)h[CNT_EVALS_SHADOW];
+  ctx->stats.sdf_evals_normals = (int64_t)h[CNT_EVALS_NORMALS];
+  ctx->stats.bulb_iters_extend = (int64_t)h[CNT_BULB_ITERS_EXTEND];
+  ctx->stats.bulb_iters_shadow = (int64_t)h[CNT_BULB_ITERS_SHADOW];
   {
     int64_t paths = 0;
-    for (int idx : my_tiles) {
-      const int tx = idx / fr.nty, ty = idx % fr.nty;
-      const int tw = std::min(tx * f->tile_w + f->tile_w, f->width) - tx * f->tile_w;
-      const int th = std::min(ty * f->tile_h + f->tile_h, f->height) - ty * f->tile_h;
-      paths += (int64_t)tw * th * spp;
+    for (int idx : ctx->job_tiles) {
+      const int tx = idx / ctx->job_nty, ty = idx % ctx->job_nty;
+      const int tw = std::min(tx * ctx->job_tw + ctx->job_tw, ctx->job_w) - tx * ctx->job_tw;
+      const int th = std::min(ty * ctx->job_th + ctx->job_th, ctx->job_h) - ty * ctx->job_th;
+      paths += (int64_t)tw * th * ctx->job_spp;
     }
     ctx->stats.paths = paths;
   }
@@ -546,7 +722,253 @@ int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const R
   return RAYN_OK;
 }
 
-// ---- multi-GPU film gather helpers ------------------------------------------------------------------
+static int32_t check_planes(RaynContext* ctx, const RaynFilmPlanes* out, bool need_all) {
+  if (!out) return fail(ctx, RAYN_ERR_INVALID_ARG, "out is NULL");
+  if (!out->color && !out->alpha && !out->background && !out->normal) return fail(ctx, RAYN_ERR_INVALID_ARG, "every film plane is NULL");
+  if (need_all && (!out->color || !out->alpha || !out->background || !out->normal))
+    return fail(ctx, RAYN_ERR_INVALID_ARG, "a gathered device-space film needs all four planes");
+  return RAYN_OK;
+}
+
+// ---- NCCL plumbing ---------------------------------------------------------------------------------------
+static int32_t nccl_load(RaynContext* ctx) {
+  if (g_nccl.handle) return RAYN_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);  // the copy already mapped by the host process (e.g. torch's) wins by soname
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(ctx, RAYN_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+  NcclApi a;
+  a.handle = h;
+#define SYM(field, name)                                                                     \
+  *(void**)(&a.field) = dlsym(h, name);                                                      \
+  if (!a.field) return fail(ctx, RAYN_ERR_NCCL, "libnccl.so.2 lacks %s", name);
+  SYM(GetUniqueId, "ncclGetUniqueId")
+  SYM(CommInitRank, "ncclCommInitRank")
+  SYM(CommInitAll, "ncclCommInitAll")
+  SYM(CommDestroy, "ncclCommDestroy")
+  SYM(AllGather, "ncclAllGather")
+  SYM(GroupStart, "ncclGroupStart")
+  SYM(GroupEnd, "ncclGroupEnd")
+  SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  g_nccl = a;
+  return RAYN_OK;
+}
+
+// shard tables + slab storage for a film geometry (uploaded once per geometry, not per frame)
+static int32_t comm_prepare(RaynContext* ctx, int W, int H, int tw, int th) {
+  RaynComm& c = ctx->comm;
+  if (c.W == W && c.H == H && c.tw == tw && c.th == th && c.d_table) return RAYN_OK;
+  CU(cudaSetDevice(ctx->device));
+  c.shards.clear();
+  size_t per = 0;
+  for (int r = 0; r < c.world; ++r) {
+    c.shards.push_back(shard_of(W, H, tw, th, r, c.world));
+    per = std::max(per, c.shards.back().size());
+  }
+  per = std::max<size_t>(per, 1);
+  std::vector<int> table((size_t)c.world * per, -1);
+  for (int r = 0; r < c.world; ++r) std::copy(c.shards[r].begin(), c.shards[r].end(), table.begin() + (size_t)r * per);
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaFree(c.d_table);
+  c.d_table = nullptr;
+  CU(cudaMalloc(&c.d_table, table.size() * sizeof(int)));
+  CU(cudaMemcpy(c.d_table, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CU(regrow(&c.d_slabs, &c.cap_slabs, (size_t)c.world * per * 10 * tw * th));
+  c.W = W, c.H = H, c.tw = tw, c.th = th, c.per_rank = (int)per;
+  return RAYN_OK;
+}
+
+// pack this rank's tiles into its slab, all-gather in place, ONE unpack kernel over the peers' slabs: all on the render
+// stream, zero host synchronisation.  in_group: the caller brackets several contexts with ncclGroupStart/End.
+static int32_t gather_pack(RaynContext* ctx, const RaynFilmPlanes* pl) {
+  RaynComm& c = ctx->comm;
+  int ntx, nty;
+  tile_grid_of(c.W, c.H, c.tw, c.th, &ntx, &nty);
+  k_film_slab<<<c.per_rank, 256, 0, ctx->stream>>>(c.W, c.H, c.tw, c.th, nty, c.d_table, c.per_rank, c.rank, -1, 0, c.d_slabs, pl->color, pl->alpha,
+                                                   pl->background, pl->normal);
+  ctx->stats.launches++;
+  return RAYN_OK;
+}
+static int32_t gather_collective(RaynContext* ctx) {
+  RaynComm& c = ctx->comm;
+  const size_t count = (size_t)c.per_rank * 10 * c.tw * c.th;
+  NC(g_nccl.AllGather(c.d_slabs + (size_t)c.rank * count, c.d_slabs, count, kNcclFloat, c.comm, ctx->stream));
+  return RAYN_OK;
+}
+static int32_t gather_unpack(RaynContext* ctx, const RaynFilmPlanes* pl) {
+  RaynComm& c = ctx->comm;
+  int ntx, nty;
+  tile_grid_of(c.W, c.H, c.tw, c.th, &ntx, &nty);
+  k_film_slab<<<c.world * c.per_rank, 256, 0, ctx->stream>>>(c.W, c.H, c.tw, c.th, nty, c.d_table, c.per_rank, 0, c.rank, 1, c.d_slabs, pl->color,
+                                                             pl->alpha, pl->background, pl->normal);
+  ctx->stats.launches++;
+  CU(cudaGetLastError());
+  return RAYN_OK;
+}
+static int32_t gather_enqueue(RaynContext* ctx, int W, int H, int tw, int th, const RaynFilmPlanes* pl, bool in_group) {
+  (void)in_group;
+  if (!ctx->comm.comm) return fail(ctx, RAYN_ERR_INVALID_ARG, "no communicator: call rayn_b200_comm_init_rank / comm_init_all first");
+  int32_t rc = comm_prepare(ctx, W, H, tw, th);
+  if (rc) return rc;
+  CU(cudaSetDevice(ctx->device));
+  timed_begin(ctx, RAYN_K_GATHER);
+  if ((rc = gather_pack(ctx, pl))) return rc;
+  if ((rc = gather_collective(ctx))) return rc;
+  if ((rc = gather_unpack(ctx, pl))) return rc;
+  timed_end(ctx, RAYN_K_GATHER, 0);
+  return RAYN_OK;
+}
+
+extern "C" {
+
+int32_t rayn_b200_render_frame(RaynContext* ctx, const RaynFrameDesc* f, const RaynFilmPlanes* out) {
+  if (!ctx) return fail(nullptr, RAYN_ERR_INVALID_ARG, "ctx is NULL");
+  int32_t rc = check_planes(ctx, out, false);
+  if (rc) return rc;
+  if ((rc = render_enqueue(ctx, f, out, nullptr, nullptr))) return rc;
+  if ((rc = copy_out_enqueue(ctx, out))) {
+    render_finish(ctx);
+    return rc;
+  }
+  return render_finish(ctx);
+}
+
+int32_t rayn_b200_sync(RaynContext* ctx) {
+  if (!ctx) return fail(nullptr, RAYN_ERR_INVALID_ARG, "ctx is NULL");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return RAYN_OK;
+}
+
+// ---- communicator ------------------------------------------------------------------------------------------
+int32_t rayn_b200_comm_unique_id(uint8_t* out_id) {
+  RaynContext* ctx = nullptr;
+  if (!out_id) return fail(nullptr, RAYN_ERR_INVALID_ARG, "out_id is NULL");
+  int32_t rc = nccl_load(nullptr);
+  if (rc) return rc;
+  ncclUniqueId id;
+  NC(g_nccl.GetUniqueId(&id));
+  memcpy(out_id, id.internal, RAYN_COMM_ID_BYTES);
+  return RAYN_OK;
+}
+int32_t rayn_b200_comm_init_rank(RaynContext* ctx, const uint8_t* id_bytes, int32_t rank, int32_t world) {
+  if (!ctx || !id_bytes) return fail(ctx, RAYN_ERR_INVALID_ARG, "comm_init_rank: NULL argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail(ctx, RAYN_ERR_INVALID_ARG, "comm_init_rank: rank %d of %d", rank, world);
+  int32_t rc = nccl_load(ctx);
+  if (rc) return rc;
+  rayn_b200_comm_destroy(ctx);
+  CU(cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  memcpy(id.internal, id_bytes, RAYN_COMM_ID_BYTES);
+  NC(g_nccl.CommInitRank(&ctx->comm.comm, world, id, rank));
+  ctx->comm.rank = rank, ctx->comm.world = world;
+  return RAYN_OK;
+}
+int32_t rayn_b200_comm_init_all(RaynContext* const* ctxs, int32_t n) {
+  RaynContext* ctx = (ctxs && n > 0) ? ctxs[0] : nullptr;
+  if (!ctx) return fail(nullptr, RAYN_ERR_INVALID_ARG, "comm_init_all: no contexts");
+  int32_t rc = nccl_load(ctx);
+  if (rc) return rc;
+  std::vector<int> devs(n);
+  std::vector<ncclComm_t> comms(n, nullptr);
+  for (int i = 0; i < n; ++i) {
+    if (!ctxs[i]) return fail(ctx, RAYN_ERR_INVALID_ARG, "comm_init_all: ctxs[%d] is NULL", i);
+    for (int j = 0; j < i; ++j)
+      if (ctxs[j]->device == ctxs[i]->device) return fail(ctx, RAYN_ERR_INVALID_ARG, "comm_init_all: device %d used twice", ctxs[i]->device);
+    rayn_b200_comm_destroy(ctxs[i]);
+    devs[i] = ctxs[i]->device;
+  }
+  NC(g_nccl.CommInitAll(comms.data(), n, devs.data()));
+  for (int i = 0; i < n; ++i) ctxs[i]->comm.comm = comms[i], ctxs[i]->comm.rank = i, ctxs[i]->comm.world = n;
+  return RAYN_OK;
+}
+int32_t rayn_b200_comm_info(const RaynContext* ctx, int32_t* rank, int32_t* world) {
+  if (!ctx) return RAYN_ERR_INVALID_ARG;
+  if (rank) *rank = ctx->comm.rank;
+  if (world) *world = ctx->comm.comm ? ctx->comm.world : 0;
+  return RAYN_OK;
+}
+int32_t rayn_b200_shard_tiles(int32_t W, int32_t H, int32_t tw, int32_t th, int32_t rank, int32_t world, int32_t* out, int32_t cap) {
+  if (W <= 0 || H <= 0 || tw <= 0 || th <= 0 || world < 1 || rank < 0 || rank >= world) return -1;
+  const std::vector<int> v = shard_of(W, H, tw, th, rank, world);
+  if (out && cap >= (int32_t)v.size()) std::copy(v.begin(), v.end(), out);
+  return (int32_t)v.size();
+}
+
+int32_t rayn_b200_film_gather(RaynContext* ctx, int32_t W, int32_t H, int32_t tw, int32_t th, const RaynFilmPlanes* pl) {
+  if (!ctx) return fail(nullptr, RAYN_ERR_INVALID_ARG, "ctx is NULL");
+  if (W <= 0 || H <= 0 || tw <= 0 || th <= 0) return fail(ctx, RAYN_ERR_INVALID_ARG, "film_gather: bad geometry");
+  int32_t rc = check_planes(ctx, pl, true);
+  if (rc) return rc;
+  if (pl->space != RAYN_MEM_DEVICE) return fail(ctx, RAYN_ERR_INVALID_ARG, "film_gather: planes must be device pointers");
+  return gather_enqueue(ctx, W, H, tw, th, pl, false);
+}
+
+int32_t rayn_b200_render_frame_sharded(RaynContext* ctx, const RaynFrameDesc* f, const RaynFilmPlanes* out) {
+  if (!ctx) return fail(nullptr, RAYN_ERR_INVALID_ARG, "ctx is NULL");
+  if (!ctx->comm.comm) return fail(ctx, RAYN_ERR_INVALID_ARG, "render_frame_sharded: no communicator on this context");
+  if (!f) return fail(ctx, RAYN_ERR_INVALID_ARG, "frame is NULL");
+  int32_t rc = check_planes(ctx, out, out && out->space == RAYN_MEM_DEVICE);
+  if (rc) return rc;
+  const std::vector<int> tiles = shard_of(f->width, f->height, f->tile_w, f->tile_h, ctx->comm.rank, ctx->comm.world);
+  RaynFilmPlanes dev;
+  if ((rc = render_enqueue(ctx, f, out, &tiles, &dev))) return rc;
+  rc = gather_enqueue(ctx, f->width, f->height, f->tile_w, f->tile_h, &dev, false);
+  if (!rc) rc = copy_out_enqueue(ctx, out);
+  const int32_t rc2 = render_finish(ctx);
+  return rc ? rc : rc2;
+}
+
+int32_t rayn_b200_render_frame_multi(RaynContext* const* ctxs, int32_t n, const RaynFrameDesc* f, const RaynFilmPlanes* out) {
+  RaynContext* ctx = (ctxs && n > 0) ? ctxs[0] : nullptr;
+  if (!ctx) return fail(nullptr, RAYN_ERR_INVALID_ARG, "render_frame_multi: no contexts");
+  if (!f || !out) return fail(ctx, RAYN_ERR_INVALID_ARG, "frame/out is NULL");
+  if (f->input_space != RAYN_MEM_HOST || out->space != RAYN_MEM_HOST)
+    return fail(ctx, RAYN_ERR_INVALID_ARG, "render_frame_multi: frame inputs and film planes must be host pointers");
+  int32_t rc = check_planes(ctx, out, false);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i)
+    if (!ctxs[i] || !ctxs[i]->comm.comm || ctxs[i]->comm.world != n || ctxs[i]->comm.rank != i)
+      return fail(ctx, RAYN_ERR_INVALID_ARG, "render_frame_multi: contexts must come from comm_init_all(ctxs, %d) in the same order", n);
+  std::vector<RaynFilmPlanes> dev(n);
+  RaynFilmPlanes scratch = *out;  // host-space marker: every context renders into its own device planes
+  int32_t first_err = RAYN_OK;
+  for (int i = 0; i < n && !first_err; ++i) {
+    const std::vector<int> tiles = shard_of(f->width, f->height, f->tile_w, f->tile_h, i, n);
+    first_err = render_enqueue(ctxs[i], f, &scratch, &tiles, &dev[i]);
+    if (first_err && ctxs[i] != ctx) fail(ctx, first_err, "GPU %d: %s", ctxs[i]->device, ctxs[i]->err.c_str());
+  }
+  if (!first_err) {
+    for (int i = 0; i < n && !first_err; ++i) {
+      first_err = comm_prepare(ctxs[i], f->width, f->height, f->tile_w, f->tile_h);
+      if (!first_err) {
+        cudaSetDevice(ctxs[i]->device);
+        first_err = gather_pack(ctxs[i], &dev[i]);
+      }
+    }
+    if (!first_err) {
+      g_nccl.GroupStart();
+      for (int i = 0; i < n && !first_err; ++i) {
+        cudaSetDevice(ctxs[i]->device);
+        first_err = gather_collective(ctxs[i]);
+      }
+      const int gr = g_nccl.GroupEnd();
+      if (!first_err && gr) first_err = fail(ctx, RAYN_ERR_NCCL, "ncclGroupEnd: %s", g_nccl.GetErrorString(gr));
+    }
+    for (int i = 0; i < n && !first_err; ++i) {
+      cudaSetDevice(ctxs[i]->device);
+      first_err = gather_unpack(ctxs[i], &dev[i]);
+    }
+    if (!first_err) first_err = copy_out_enqueue(ctx, out);
+  }
+  for (int i = 0; i < n; ++i) {
+    const int32_t rc2 = render_finish(ctxs[i]);
+    if (!first_err && rc2) first_err = rc2;
+  }
+  return first_err;
+}
+
+// ---- explicit slab helpers --------------------------------------------------------------------------------------
 int64_t rayn_b200_film_slab_floats(int32_t tw, int32_t th, int32_t n_tiles) {
   if (tw <= 0 || th <= 0 || n_tiles < 0) return -1;
   return (int64_t)n_tiles * 10 * tw * th;
@@ -557,14 +979,14 @@ static int32_t pack_unpack(RaynContext* ctx, int W, int H, int tw, int th, const
     return fail(ctx, RAYN_ERR_INVALID_ARG, "film pack/unpack: bad argument");
   if (n == 0) return RAYN_OK;
   CU(cudaSetDevice(ctx->device));
-  const int ntx = (W + W % tw) / tw, nty = (H + H % th) / th;
+  int ntx, nty;
+  tile_grid_of(W, H, tw, th, &ntx, &nty);
   for (int i = 0; i < n; ++i)
     if (tile_list[i] < 0 || tile_list[i] >= ntx * nty) return fail(ctx, RAYN_ERR_INVALID_ARG, "film pack/unpack: tile %d out of range", tile_list[i]);
   CU(regrow(&ctx->d_pack_ids, &ctx->cap_pack_ids, (size_t)n));
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpyAsync(ctx->d_pack_ids, tile_list, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  k_film_pack<<<n, 256, 0, ctx->stream>>>(W, H, tw, th, nty, ctx->d_pack_ids, pl->color, pl->alpha, pl->background, pl->normal, slab, unpack,
-                                          pl->color, pl->alpha, pl->background, pl->normal);
+  k_film_slab<<<n, 256, 0, ctx->stream>>>(W, H, tw, th, nty, ctx->d_pack_ids, n, 0, -1, unpack, slab, pl->color, pl->alpha, pl->background, pl->normal);
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(ctx->stream));
   return RAYN_OK;
@@ -662,6 +1084,33 @@ int32_t rayn_b200_kat_sdf_dist(RaynContext* ctx, const RaynHitable* sdf, int64_t
   CU(e);
   k_kat_sdf_dist<<<blocks, 128, 0, ctx->stream>>>(*sdf, n, dp, dout);
   KAT_EPILOGUE(out, dout, n, float)
+  return RAYN_OK;
+}
+int32_t rayn_b200_kat_sdf_dist2(RaynContext* ctx, const RaynHitable* sdf, int32_t variant, int64_t n, const float* points3, float* out) {
+  KAT_PROLOGUE
+  if (!sdf || !points3 || !out) return fail(ctx, RAYN_ERR_INVALID_ARG, "kat_sdf_dist2: NULL");
+  if (sdf->kind == RAYN_HITABLE_SPHERE) return fail(ctx, RAYN_ERR_INVALID_ARG, "kat_sdf_dist2: not an SDF");
+  int v = variant < 0 ? sdf_variant(*sdf) : variant;
+  if (v >= SDFV_COUNT || (v == SDFV_BULB) != (sdf->kind == RAYN_HITABLE_MANDELBULB) ||
+      ((v == SDFV_BOX_12_FAST || v == SDFV_BOX_N_FAST) && !sdf_box_fast_ok(*sdf)) || (v == SDFV_BOX_12_FAST && sdf->iterations != 12))
+    return fail(ctx, RAYN_ERR_INVALID_ARG, "kat_sdf_dist2: variant %d does not fit the hitable", v);
+  float* dp = tmp.up(points3, 3 * n, &e);
+  float* dout = tmp.up<float>(nullptr, n, &e);
+  CU(e);
+  DISPATCH_SDFV(v, (k_kat_sdf_dist2<V><<<(unsigned)((n / 2 + 128) / 128), 128, 0, ctx->stream>>>(*sdf, 1.0f, n, dp, dout)));
+  KAT_EPILOGUE(out, dout, n, float)
+  return RAYN_OK;
+}
+int32_t rayn_b200_kat_fastdiv(RaynContext* ctx, float num, uint32_t first_bits, int64_t n, int64_t* out_mismatches) {
+  if (!ctx || !out_mismatches || n < 0) return fail(ctx, RAYN_ERR_INVALID_ARG, "kat_fastdiv: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemsetAsync(ctx->d_kat, 0, sizeof(unsigned long long), ctx->stream));
+  if (n > 0) k_kat_fastdiv<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(num, first_bits, n, ctx->d_kat);
+  CU(cudaGetLastError());
+  unsigned long long h = 0;
+  CU(cudaMemcpyAsync(&h, ctx->d_kat, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *out_mismatches = (int64_t)h;
   return RAYN_OK;
 }
 int32_t rayn_b200_kat_sdf_hit(RaynContext* ctx, const RaynHitable* sdf, const RaynRenderConsts* consts, int64_t n, const float* origins3,

@@ -70,13 +70,34 @@ DM_HD double i2d(int64_t u) {
 }
 
 // ---- exactly-defined float helpers -------------------------------------------------
-// Explicit single-rounding fused multiply-add: the reference's `mul_add`
-// (src/sdf.rs:45,134-135,161; src/ray.rs:23; src/math.rs:203-204,210; src/light.rs:99).
+// Explicit single-rounding fused multiply-add.  Used directly only where the arithmetic is OURS to
+// define (the authored Mandelbulb, the float-only transcendental cores below).
 DM_HD float fma(float a, float b, float c) {
 #ifdef __CUDA_ARCH__
   return __fmaf_rn(a, b, c);
 #else
   return __builtin_fmaf(a, b, c);
+#endif
+}
+// `wide` 0.4.6 `f32x4::mul_add` — what the reference writes at src/sdf.rs:45,134-135,161; src/ray.rs:23;
+// src/math.rs:203-204,210; src/light.rs:99 and what ultraviolet's dot / cross / mag_sq are built from.
+// That crate fuses only under `cfg(target_feature = "fma")`; the reference builds with a plain
+// `cargo run --release` (README.md:42-44, Cargo.toml:10-14: no RUSTFLAGS, no .cargo/config), so the x86-64
+// baseline target has no `fma` feature and mul_add is `(a * b) + c` with TWO roundings.  That is the default here
+// (RAYN_MULADD_FUSED = 0).  RAYN_MULADD_FUSED = 1 builds the variant a `-C target-feature=+fma` rayn would give;
+// kernels, oracle and golden fixtures exist for both (oracle/README.md A6).
+#ifndef RAYN_MULADD_FUSED
+#define RAYN_MULADD_FUSED 0
+#endif
+DM_HD float mul_add(float a, float b, float c) {
+#if RAYN_MULADD_FUSED
+  return dm::fma(a, b, c);
+#else
+#ifdef __CUDA_ARCH__
+  return __fadd_rn(__fmul_rn(a, b), c);  // never contracted, whatever --fmad says
+#else
+  return a * b + c;  // host TUs are compiled with -ffp-contract=off
+#endif
 #endif
 }
 // SSE minps/maxps semantics (`wide` f32x4::min/max): second operand on NaN.

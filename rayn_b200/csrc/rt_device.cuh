@@ -29,10 +29,10 @@ RT_D f3 operator*(f3 a, f3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
 RT_D f3 operator*(f3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
 RT_D f3 operator/(f3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
 RT_D f3 operator-(f3 a) { return {-a.x, -a.y, -a.z}; }
-RT_D f3 fma3(f3 a, f3 b, f3 c) { return {dm::fma(a.x, b.x, c.x), dm::fma(a.y, b.y, c.y), dm::fma(a.z, b.z, c.z)}; }
-RT_D f3 fma3s(f3 a, float s, f3 c) { return {dm::fma(a.x, s, c.x), dm::fma(a.y, s, c.y), dm::fma(a.z, s, c.z)}; }
+RT_D f3 fma3(f3 a, f3 b, f3 c) { return {dm::mul_add(a.x, b.x, c.x), dm::mul_add(a.y, b.y, c.y), dm::mul_add(a.z, b.z, c.z)}; }
+RT_D f3 fma3s(f3 a, float s, f3 c) { return {dm::mul_add(a.x, s, c.x), dm::mul_add(a.y, s, c.y), dm::mul_add(a.z, s, c.z)}; }
 // ultraviolet Wec3::dot / mag / normalized / cross / reflected (oracle/README.md A1-A5)
-RT_D float dot(f3 a, f3 b) { return dm::fma(a.x, b.x, dm::fma(a.y, b.y, a.z * b.z)); }
+RT_D float dot(f3 a, f3 b) { return dm::mul_add(a.x, b.x, dm::mul_add(a.y, b.y, a.z * b.z)); }
 RT_D float mag_sq(f3 a) { return dot(a, a); }
 RT_D float mag(f3 a) { return sqrtf(dot(a, a)); }
 RT_D f3 normalized(f3 a) {
@@ -40,7 +40,7 @@ RT_D f3 normalized(f3 a) {
   return a * r;
 }
 RT_D f3 cross(f3 a, f3 b) {
-  return {dm::fma(a.y, b.z, -(a.z * b.y)), dm::fma(a.z, b.x, -(a.x * b.z)), dm::fma(a.x, b.y, -(a.y * b.x))};
+  return {dm::mul_add(a.y, b.z, -(a.z * b.y)), dm::mul_add(a.z, b.x, -(a.x * b.z)), dm::mul_add(a.x, b.y, -(a.y * b.x))};
 }
 RT_D f3 reflected(f3 v, f3 n) { return v - n * (2.0f * dot(v, n)); }
 RT_D float component_max(f3 a) { return dm::max(dm::max(a.x, a.y), a.z); }
@@ -69,11 +69,11 @@ RT_D m3 onb(f3 nor) {
 
 // math.rs:201-219 concentric_circle_map
 RT_D void concentric(float u0, float u1, float* ox, float* oy) {
-  float a = dm::fma(u0, 2.0f, -1.0f);
-  float b = dm::fma(u1, 2.0f, -1.0f);
+  float a = dm::mul_add(u0, 2.0f, -1.0f);
+  float b = dm::mul_add(u1, 2.0f, -1.0f);
   if (a == 0.0f && b == 0.0f) b = 0.0001f;
   float phi1 = RT_FRAC_PI_4 * b / a;
-  float phi2 = dm::fma(-RT_FRAC_PI_4 / b, a, RT_FRAC_PI_2);
+  float phi2 = dm::mul_add(-RT_FRAC_PI_4 / b, a, RT_FRAC_PI_2);
   bool mask = (a * a) > (b * b);
   float r = mask ? a : b;
   float phi = mask ? phi1 : phi2;
@@ -86,7 +86,7 @@ RT_D void concentric(float u0, float u1, float* ox, float* oy) {
 RT_D f3 cosine_weighted(float u0, float u1) {
   float x, y;
   concentric(u0, u1, &x, &y);
-  float msq = dm::fma(x, x, y * y);
+  float msq = dm::mul_add(x, x, y * y);
   float z = sqrtf(1.0f - dm::min(msq, 1.0f));
   return {x, y, z};
 }
@@ -106,7 +106,8 @@ RT_D float f_schlick(float cosv, float f0) { return f0 + (1.0f - f0) * dm::powi5
 // Scene as a kernel-parameter block (constant bank: warp-uniform operands cost no load)
 // ------------------------------------------------------------------------------------------
 struct DevScene {
-  int32_t n_hit, n_mat, n_lights, pad0;
+  int32_t n_hit, n_mat, n_lights;
+  float one;  // 1.0f, set at upload: a multiplier the compiler cannot constant-fold (rt_sdf2.cuh::muladd2)
   RaynHitable hit[RAYN_MAX_HITABLES];
   RaynMaterial mat[RAYN_MAX_MATERIALS];
   RaynLight light[RAYN_MAX_LIGHTS];
@@ -195,15 +196,15 @@ RT_D void eval_step(SdfEval& e, const RaynHitable& h) {
       cy = dm::min(dm::max(p.y, nl), l);
       cz = dm::min(dm::max(p.z, nl), l);
     }
-    p.x = dm::fma(cx, 2.0f, -p.x);
-    p.y = dm::fma(cy, 2.0f, -p.y);
-    p.z = dm::fma(cz, 2.0f, -p.z);
+    p.x = dm::mul_add(cx, 2.0f, -p.x);
+    p.y = dm::mul_add(cy, 2.0f, -p.y);
+    p.z = dm::mul_add(cz, 2.0f, -p.z);
     const float r2 = mag_sq(p);
     const float mul = dm::max(1.0f, h.fixed_rad_sq / dm::max(h.min_rad_sq, r2));
     p = p * mul;
     e.dr = e.dr * mul;
     e.w = fma3s(p, h.scale, e.c);
-    e.dr = dm::fma(-e.dr, h.scale, 1.0f);
+    e.dr = dm::mul_add(-e.dr, h.scale, 1.0f);
   }
   ++e.it;
 }
@@ -406,7 +407,7 @@ RT_D void light_sample_volume(const RaynLight& L, float sample, f3 ray_o, f3 ray
   float th = theta_a * (1.0f - sample) + theta_b * sample;  // Lerp (A7)
   float t = d * dm::tan(th);
   *out_dist = delta + t;
-  *out_pdf = d / ((theta_b - theta_a) * dm::fma(d, d, t * t));
+  *out_pdf = d / ((theta_b - theta_a) * dm::mul_add(d, d, t * t));
 }
 
 // ---- BSDFs, material.rs ---------------------------------------------------------------------------

@@ -15,8 +15,16 @@
 //                         (hitable.rs:94-133)
 //   g = ts*R + id, id = (xl*th + yl)*spp + sample  — the reference's raygen order
 //   `for x { for y { for samp { 4 lanes } } }` (film.rs:456-464).
+//
+// Kernel sequence of a pass: k_raygen, then per depth
+//   k_scan_live -> k_extend_spheres / k_extend_march<V> (fold order of hitable.rs:177-198) -> k_bin
+//   -> k_normals<V> (one per SDF hitable) -> k_shade_pre -> k_shadow<V> (one per SDF hitable)
+//   -> k_shade_post -> k_compact;  finally k_resolve.
+// The two march kernels and k_normals evaluate the distance field on TWO points per thread with the packed
+// f32x2 arithmetic of sm_100a (rt_sdf2.cuh).
 #pragma once
 #include "rt_device.cuh"
+#include "rt_sdf2.cuh"
 
 namespace rt {
 
@@ -48,24 +56,32 @@ struct PassBufs {
   int* n_slots;    // [n_tiles]
   int* bin_start;  // [n_tiles*(RAYN_MAX_HITABLES+1)]
   unsigned long long* counters;  // [8] stats
-  // v3 shading split (pre -> persistent shadow march -> post)
+  // shading split (normals -> pre -> persistent shadow march -> post)
   float4* nrm;        // [paths] shading normal.xyz, offset_by of the current depth (hitable.rs:21-28)
   uint32_t* vis;      // [paths] bit i = light sample i of this depth is visible
-  float4* seg_a;      // [seg_cap] shadow segment start.xyz, max_dist
-  float4* seg_b;      // [seg_cap] dir.xyz, bits(sample i | hitable << 8)
-  int* seg_owner;     // [seg_cap] path index g
-  int* seg_count;     // [1] segments pushed this depth
-  long long seg_cap;
+  // shadow segments of the current depth, one queue per SDF hitable (ordinal j): entries [j*seg_cap, j*seg_cap + seg_count[j])
+  float4* seg_a;      // start.xyz, max_dist
+  float4* seg_b;      // dir.xyz, bits(path index g << 4 | light-sample bit)
+  int* seg_count;     // [RAYN_MAX_HITABLES] segments pushed this depth, per SDF ordinal
+  long long seg_cap;  // capacity of ONE queue
   float4* lc_c;       // [paths * lc_ns] unoccluded light contribution c.xyz and its denominator (pdf), per light sample of this depth
   float* lc_t;        // [paths * 8] volume rounds only: transmission to the scatter point (integrator.rs:122-126)
   int lc_ns;          // light samples per path per depth: 4, or 4 * (1 + vm) with volumetrics
 };
 
-enum { CNT_EXTEND_RAYS = 0, CNT_SHADE_LANES = 1, CNT_SHADOW_RAYS = 2, CNT_EVALS_EXTEND = 3, CNT_EVALS_SHADOW = 4 };
+enum { CNT_EXTEND_RAYS = 0, CNT_SHADE_LANES = 1, CNT_SHADOW_RAYS = 2, CNT_EVALS_EXTEND = 3, CNT_EVALS_SHADOW = 4,
+       CNT_BULB_ITERS_EXTEND = 5, CNT_BULB_ITERS_SHADOW = 6, CNT_EVALS_NORMALS = 7, CNT_TOTAL = 8 };  // Mandelbulb iterations actually run (the count is data dependent)
+
+// global work counters of the persistent kernels (RaynContext::d_work_ctr), zeroed by k_scan_live every depth
+enum { WC_EXTEND = 0, WC_SHADOW = 1 /* + SDF ordinal */, WC_SEG_COUNT = 1 + RAYN_MAX_HITABLES /* + SDF ordinal */, WC_TOTAL = 1 + 2 * RAYN_MAX_HITABLES };
 
 #define TERM_NONE 0u
 #define TERM_COLOR 1u
 #define TERM_BACKGROUND 2u
+// term word: kind (2 bits) | depth (8 bits) | shading slot (22 bits).  The low 30 bits are the film-accumulation key.
+#define TERM_DEPTH_SHIFT 22
+#define TERM_MAX_SLOTS (1 << TERM_DEPTH_SHIFT)
+#define TERM_MAX_DEPTH 255
 
 struct TileGeom {
   int x0, y0, tw, th, npaths;
@@ -90,6 +106,12 @@ RT_D float samp2(const DevFrame& fr, int dim, int sample, float scramble, int se
   return dm::fract(__ldg(fr.s2 + dim + (size_t)sample * 2 + (size_t)fr.spp * 2 * set) + scramble);
 }
 
+// same for a partially active warp (callers that returned early)
+RT_D void warp_add_partial(unsigned long long* ctr, int v) {
+  const unsigned m = __activemask();
+  const int s = __reduce_add_sync(m, v);
+  if ((int)(threadIdx.x & 31) == __ffs(m) - 1 && s) atomicAdd(ctr, (unsigned long long)s);
+}
 RT_D void warp_add(unsigned long long* ctr, int v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   if ((threadIdx.x & 31) == 0 && v) atomicAdd(ctr, (unsigned long long)v);
@@ -127,33 +149,6 @@ __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ DevScene
   pb.nrm0[g] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
   pb.term[g] = 0u;
   pb.q_live[g] = i;
-}
-
-// ------------------------------------------------------------------------------------------
-// K2 extend: HitableStore::add_hits (hitable.rs:170-210) incl. the sphere-march
-// (sdf.rs:59-83).  One thread per live ray: reads float4 o_time + float4 d, writes t + key.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_extend(const __grid_constant__ DevScene sc, const PassBufs pb, const Thr thr) {
-  const int ts = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = pb.n_live[ts];
-  if ((i & ~31) >= n) return;
-  int evals = 0;
-  const bool act = i < n;
-  if (act) {
-    const size_t q = (size_t)ts * pb.R + i;
-    const int id = pb.q_live[q];
-    const size_t g = (size_t)ts * pb.R + id;
-    const float4 o4 = pb.o_time[g];
-    const float4 d4 = pb.d_t[g];
-    float t;
-    int obj;
-    closest_hit(sc, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z), thr, &t, &obj, &evals);
-    pb.d_t[g].w = t;
-    pb.q_key[q] = obj;
-  }
-  warp_add(pb.counters + CNT_EXTEND_RAYS, act ? 1 : 0);
-  warp_add(pb.counters + CNT_EVALS_EXTEND, evals);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -222,280 +217,10 @@ __global__ void __launch_bounds__(BIN_T) k_bin(const PassBufs pb, const int n_hi
     for (int k = start[tid] + cnt[tid]; k < start[tid + 1]; ++k) qs[k] = -1;  // Ray::new_invalid padding
 }
 
-// ------------------------------------------------------------------------------------------
-// K4 shade (+K5 shadow fused): get_shading_info (sdf.rs:85-101 / sphere.rs:74-86), sample
-// draw (film.rs:564-589), PathTracingIntegrator::integrate (integrator.rs:47-205).
-// One thread per shading slot; lanes 4k..4k+3 of a warp are exactly one reference packet and
-// exchange their light choices with __shfl_sync.
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_shade(const __grid_constant__ DevScene sc, const DevFrame fr, const PassBufs pb,
-                                               const int depth, const Thr thr) {
-  const int ts = blockIdx.y;
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  const int nslots = pb.n_slots[ts];
-  if ((s & ~31) >= nslots) return;  // warp-uniform
-  const int lane = threadIdx.x & 31;
-  int* __restrict__ qs = pb.q_shade + (size_t)ts * pb.QS;
-  const int id = s < nslots ? qs[s] : -1;
-  const bool valid = id >= 0;
-  const TileGeom tg = tile_geom(fr, pb.tile_ids[ts]);
-  // sample index / scramble: padded lanes are Ray::new_invalid -> sample 0, scramble 0 (ray.rs:54-66)
-  int sample = 0;
-  float scramble = 0.0f;
-  int pl = 0;
-  if (valid) {
-    pl = id / fr.spp;
-    sample = id - pl * fr.spp;
-    const int xl = pl / tg.th, yl = pl - xl * tg.th;
-    scramble = __ldg(fr.scramble + (tg.x0 + xl) + (size_t)(tg.y0 + yl) * fr.W);
-  }
-  const int n1 = 3 + fr.vm, n2h = (12 + 8 * fr.vm) / 2;  // 1-D sets / 2-D sets per depth
-  const int set1 = 1 + depth * n1, set2 = 2 + depth * n2h;
-  const int nl = sc.n_lights;
-  // light choices: one index per lane per light-selection sample (integrator.rs:76-77,100-102)
-  unsigned pack = 0;
-  if (nl > 0) {
-    pack = (unsigned)light_index(samp1(fr, sample, scramble, set1 + 0), nl) |
-           ((unsigned)light_index(samp1(fr, sample, scramble, set1 + 1), nl) << 8) |
-           ((unsigned)light_index(samp1(fr, sample, scramble, set1 + 2), nl) << 16);
-  }
-  unsigned packs[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) packs[k] = __shfl_sync(0xffffffffu, pack, (lane & ~3) + k);
-  warp_add(pb.counters + CNT_SHADE_LANES, valid ? 1 : 0);
-  int evals = 0, shadows = 0;
-  if (valid) {
-    // object of this slot from the tile's bin table
-    const int* __restrict__ bs = pb.bin_start + ts * (RAYN_MAX_HITABLES + 1);
-    int obj = 0;
-    while (obj + 1 < sc.n_hit && s >= bs[obj + 1]) ++obj;
-    const RaynHitable& h = sc.hit[obj];
-    const RaynMaterial& mat = sc.mat[h.material];
-    const size_t g = (size_t)ts * pb.R + id;
-    const float4 o4 = pb.o_time[g], d4 = pb.d_t[g], r4 = pb.rad[g], t4 = pb.thr[g];
-    ShadingPoint sp;
-    sp.o = mk3(o4.x, o4.y, o4.z);
-    sp.d = mk3(d4.x, d4.y, d4.z);
-    sp.time = o4.w;
-    sp.t = d4.w;
-    shading_info(sc, h, thr, sp, &evals);
-    f3 radiance = mk3(r4.x, r4.y, r4.z), throughput = mk3(t4.x, t4.y, t4.z);
-    const f3 wo = -sp.d;
-    const bool has_ext = sc.vol.has_extinction != 0;
-    const float neg_rho_t = -sc.vol.coeff_extinction;
-    const float vt = has_ext ? dm::exp(neg_rho_t * sp.t) : 1.0f;  // integrator.rs:64-68
-    radiance = radiance + bsdf_le(mat, wo) * throughput * vt;        // :70-71
-    const bool recv = receives_light(mat);
-
-    if (recv && nl > 0) {  // :73-94
-      const float correction = (float)nl / 4.0f;
-#pragma unroll 1
-      for (int i = 0; i < 4; ++i) {
-        const int li_idx = (int)(packs[i] & 0xffu);
-        const float u0 = samp2(fr, 0, sample, scramble, set2 + i), u1 = samp2(fr, 1, sample, scramble, set2 + i);
-        // surface_sample_one_light :207-240
-        f3 end_point, li;
-        float pdf;
-        light_sample(sc.light[li_idx], u0, u1, sp.point, &end_point, &li, &pdf);
-        f3 wi = end_point - sp.point;
-        const float dist = mag(wi);
-        wi = wi / dist;
-        const f3 occlude_point = sp.point + sp.normal * dm::signum(dot(sp.normal, wi)) * sp.offset_by;
-        const float occluded = test_occluded(sc, occlude_point, end_point, &evals);
-        ++shadows;
-        const f3 f = bsdf_f(mat, wo, wi, sp.normal) * dm::max(dot(sp.normal, wi), 0.0f);
-        const float transmission = has_ext ? dm::exp(neg_rho_t * dist) : 1.0f;
-        const f3 contrib = li * f * transmission * occluded / pdf;
-        radiance = radiance + contrib * throughput * correction * vt;
-      }
-    }
-    if (sc.vol.has_scattering && nl > 0) {  // :96-132
-      const float rho_s = sc.vol.coeff_scattering;
-      const float correction = (float)nl / 4.0f / (float)fr.vm;
-      const float vol_sample = samp1(fr, sample, scramble, set1 + 1);  // samples_1d[1], :115
-#pragma unroll 1
-      for (int march = 0; march < fr.vm; ++march) {
-#pragma unroll 1
-        for (int i = 0; i < 4; ++i) {
-          const int li_idx = (int)((packs[i] >> (8 * (march + 1))) & 0xffu);
-          const int set = set2 + 4 + 4 * march + i;  // samples_2d[8 + 8*march + 2i]
-          const float u0 = samp2(fr, 0, sample, scramble, set), u1 = samp2(fr, 1, sample, scramble, set);
-          // volume_sample_one_light :242-281
-          const RaynLight& L = sc.light[li_idx];
-          float vol_dist, vol_pdf;
-          light_sample_volume(L, vol_sample, sp.o, sp.d, sp.t, &vol_dist, &vol_pdf);
-          const f3 sampled_point = sp.o + sp.d * vol_dist;
-          f3 end_point, li;
-          float light_pdf;
-          light_sample(L, u0, u1, sampled_point, &end_point, &li, &light_pdf);
-          const f3 wi = end_point - sampled_point;
-          const float dist_point_to_light = mag(wi);
-          const float occluded = test_occluded(sc, sampled_point, end_point, &evals);
-          ++shadows;
-          const float f = 1.0f / (4.0f * RT_PI);
-          const float tr_light = has_ext ? dm::exp(neg_rho_t * dist_point_to_light) : 1.0f;
-          const f3 contrib = li * f * tr_light * occluded / (vol_pdf * light_pdf);
-          const float transmission = has_ext ? dm::exp(neg_rho_t * vol_dist) : 1.0f;
-          radiance = radiance + contrib * throughput * correction * rho_s * transmission;
-        }
-      }
-    }
-
-    if (recv) {  // :134-188
-      const int setb = set2 + 4 + 4 * fr.vm;  // samples_2d[8 + 8*vm ..]
-      const Scatter se = bsdf_scatter(mat, wo, sp, samp1(fr, sample, scramble, set1 + 3), samp2(fr, 0, sample, scramble, setb),
-                                      samp2(fr, 1, sample, scramble, setb), samp2(fr, 0, sample, scramble, setb + 1),
-                                      samp2(fr, 1, sample, scramble, setb + 1));
-      const float ndl = dm::abs(dot(se.wi, sp.normal));
-      f3 new_throughput = throughput * vt * se.f * ndl / se.pdf;
-      float roulette_factor = 0.0f;
-      if (depth > 2) {
-        roulette_factor = dm::max(1.0f - component_max(throughput), 0.05f);
-        new_throughput = new_throughput / (1.0f - roulette_factor);
-      }
-      if (depth == 0)  // Alpha(1) + WorldNormal(n), :161-169
-        pb.nrm0[g] = make_float4(sp.normal.x, sp.normal.y, sp.normal.z, __uint_as_float((unsigned)s + 1u));
-      const float roulette_sample = samp1(fr, sample, scramble, set1 + 4);
-      if (depth >= fr.max_bounces || roulette_sample < roulette_factor) {
-        pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
-        pb.term[g] = (TERM_COLOR << 30) | ((unsigned)depth << 20) | (unsigned)s;
-        qs[s] = -1;
-      } else {
-        // WShadingPoint::create_rays, hitable.rs:42-47
-        const f3 no = sp.point + sp.normal * dm::signum(dot(sp.normal, se.wi)) * sp.offset_by;
-        if (!any_nan(new_throughput)) throughput = new_throughput;  // :181-183
-        pb.o_time[g] = make_float4(no.x, no.y, no.z, sp.time);
-        pb.d_t[g] = make_float4(se.wi.x, se.wi.y, se.wi.z, 0.0f);
-        pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
-        pb.thr[g] = make_float4(throughput.x, throughput.y, throughput.z, 0.0f);
-      }
-    } else {  // :189-203
-      pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
-      pb.term[g] = ((depth == 0 ? TERM_BACKGROUND : TERM_COLOR) << 30) | ((unsigned)depth << 20) | (unsigned)s;
-      qs[s] = -1;
-    }
-  }
-  warp_add(pb.counters + CNT_EVALS_SHADOW, evals);
-  warp_add(pb.counters + CNT_SHADOW_RAYS, shadows);
-}
-
-// ==========================================================================================
-// v2 march kernels: dynamic lane refill.
-//
-// ncu on v0 (profiles/r01_v0_summary.md): issue slots 82-86 % busy with only 5-7 of 32 lanes
-// active per instruction - a warp runs until its slowest march ends.  v2 keeps ONE sdf_dist()
-// call site per loop trip and hands an idle lane the next work item as soon as its march ends,
-// so every trip evaluates the distance field on (nearly) all 32 lanes.  A march result
-// depends only on its own ray, so the order in which lanes pick up work cannot change any
-// output bit.
-// ==========================================================================================
-
-// ---- K2 v2: closest hit over a 2048-ray chunk of one tile, work pulled from a shared counter ----
-#define EXT_T 128
-#define EXT_CHUNK 2048
-__global__ void __launch_bounds__(EXT_T, 6) k_extend2(const __grid_constant__ DevScene sc, const PassBufs pb, const Thr thr) {
-  const int ts = blockIdx.y;
-  const int n = pb.n_live[ts];
-  const int chunk0 = blockIdx.x * EXT_CHUNK;
-  if (chunk0 >= n) return;
-  const int chunk1 = min(chunk0 + EXT_CHUNK, n);
-  __shared__ int s_next;
-  __shared__ RaynHitable s_hit[RAYN_MAX_HITABLES];  // shared-memory staging of the SDF / sphere constants
-  if (threadIdx.x == 0) s_next = chunk0;
-  for (int k = threadIdx.x; k < sc.n_hit; k += EXT_T) s_hit[k] = sc.hit[k];
-  __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const unsigned lt = (1u << lane) - 1u;
-  const int n_hit = sc.n_hit;
-  const float S = sc.rc.sdf_detail_scale;
-  const float c0 = 0.00005f * S, c1 = 0.05f * S;
-  const int max_marches = sc.rc.max_marches;
-  const float t_max0 = sc.rc.world_radius * 2.0f;  // film.rs:556
-
-  bool have = false, marching = false, exhausted = false;
-  f3 o = {0, 0, 0}, d = {0, 0, 0};
-  float closest = 0.0f, t = 0.0f;
-  int id = -1, hidx = 0, steps = 0, evals = 0, rays = 0;
-  size_t q = 0, g = 0;
-  while (true) {
-    __syncwarp();
-    const unsigned idle = __ballot_sync(0xffffffffu, !have);
-    if (idle && !exhausted) {
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&s_next, __popc(idle));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      const int idx = base + __popc(idle & lt);
-      if (base + __popc(idle) >= chunk1) exhausted = true;
-      if (!have && idx < chunk1) {
-        q = (size_t)ts * pb.R + idx;
-        g = (size_t)ts * pb.R + pb.q_live[q];
-        const float4 o4 = pb.o_time[g], d4 = pb.d_t[g];
-        o = mk3(o4.x, o4.y, o4.z);
-        d = mk3(d4.x, d4.y, d4.z);
-        closest = t_max0;
-        id = -1;
-        hidx = 0;
-        marching = false;
-        have = true;
-        ++rays;
-      }
-    }
-    if (!__any_sync(0xffffffffu, have)) break;
-    if (have && !marching) {  // analytic hitables up to the next SDF (hitable.rs:177-198 fold order)
-      while (hidx < n_hit && s_hit[hidx].kind == RAYN_HITABLE_SPHERE) {
-        const float ts_ = sphere_hit(s_hit[hidx], o, d, closest, 0.0f);  // static scenes only (api.cu rejects motion for this family)
-        if (ts_ < closest) {
-          closest = ts_;
-          id = hidx;
-        }
-        ++hidx;
-      }
-      if (hidx >= n_hit) {
-        pb.d_t[g].w = closest;
-        pb.q_key[q] = id;
-        have = false;
-      }
-    }
-    if (have) {  // exactly one distance evaluation per trip: TracedSDF::hit, sdf.rs:59-83
-      const f3 p = marching ? fma3s(d, t, o) : o;
-      const float dd = sdf_dist(s_hit[hidx], p);
-      ++evals;
-      bool end = false;
-      if (!marching) {
-        t = dd;
-        steps = 0;
-        marching = true;
-        end = t != t;
-      } else {
-        const bool hit = dm::abs(dd) < dm::max(c0, c1 * thr.at(t));
-        const bool gt = t > closest;
-        if (hit || gt) {
-          end = true;
-        } else {
-          t = t + dd;
-          ++steps;
-          end = (t != t) || steps >= max_marches;
-        }
-      }
-      if (end) {
-        if (t < closest) {
-          closest = t;
-          id = hidx;
-        }
-        marching = false;
-        ++hidx;
-      }
-    }
-  }
-  warp_add(pb.counters + CNT_EXTEND_RAYS, rays);
-  warp_add(pb.counters + CNT_EVALS_EXTEND, evals);
-}
-
-// ---- pass-wide work distribution for the persistent march kernels.  v2 still idles lanes at the
-// tail of every 2048-ray chunk (ncu r1v2: 19 of 32 lanes at the distance-eval site), so the
-// per-tile live lists are flattened into 128-ray batches numbered across the whole pass
-// (k_scan_live builds the prefix) and resident warps pull batches from ONE global counter until
-// the pass is drained: the only tail left is at the very end of the kernel.
+// ---- pass-wide work distribution for the persistent march kernels: the per-tile live lists are
+// flattened into 128-ray batches numbered across the whole pass (k_scan_live builds the prefix) and
+// resident warps pull batches from ONE global counter until the pass is drained, so the only tail
+// is at the very end of the kernel (round-1 history of this design: DESIGN.md §4).
 #define EXT_BATCH 128
 #define SCAN_T 1024
 __global__ void __launch_bounds__(SCAN_T) k_scan_live(const PassBufs pb, int* __restrict__ batch_prefix, int* __restrict__ work_ctr) {
@@ -505,10 +230,8 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_live(const PassBufs pb, int* __
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     carry = 0;
-    work_ctr[0] = 0;  // extend batches
-    work_ctr[1] = 0;  // shadow batches
-    work_ctr[2] = 0;  // shadow segments pushed (PassBufs::seg_count)
   }
+  if (tid < WC_TOTAL) work_ctr[tid] = 0;  // extend batches, shadow batches and pushed-segment counts (PassBufs::seg_count)
   __syncthreads();
   for (int base = 0; base < pb.n_tiles; base += SCAN_T) {
     const int i = base + tid;
@@ -573,38 +296,36 @@ __global__ void __launch_bounds__(256) k_extend_spheres(const __grid_constant__ 
   if (init) warp_add(pb.counters + CNT_EXTEND_RAYS, act ? 1 : 0);
 }
 
-// TracedSDF::hit (sdf.rs:59-83) for hitable `hk` over every live ray of the pass.
-// FLAT = iteration-granular trips: one loop trip is ONE fractal iteration on every busy lane; a
-// lane whose evaluation completes runs the short epilogue (distance estimate, hit test, step)
-// in the same trip.  Used when the SDF is the Mandelbulb, whose per-evaluation iteration count
-// varies from 0 to `iterations` (ncu r1v3: 12-14 of 32 lanes active inside the iteration body
-// with evaluation-granular trips).  The arithmetic is the same SdfEval state machine either way.
-template <bool FLAT>
-__global__ void __launch_bounds__(EXT_T, 10) k_extend_march(const __grid_constant__ DevScene sc, const PassBufs pb, const Thr thr,
-                                                           const int hk, const int* __restrict__ batch_prefix, int* __restrict__ work_ctr) {
-  __shared__ RaynHitable s_h;  // shared-memory staging of the fractal constants
-  if (threadIdx.x == 0) s_h = sc.hit[hk];
-  __syncthreads();
+// ------------------------------------------------------------------------------------------
+// K2 sphere-march: TracedSDF::hit (sdf.rs:59-83) for SDF hitable `hk` over every live
+// ray of the pass.  Persistent kernel: one wave of CTAs, warps pull 128-ray batches from a global
+// counter.  Each THREAD marches TWO rays ("slots"); their state lives in float2 registers (component
+// .x = slot 0, .y = slot 1) so the distance estimator runs on the packed f32x2 pipe (rt_sdf2.cuh).
+// One loop trip = one distance evaluation on every busy slot of the warp; a slot whose march ended is
+// refilled at the top of the next trip, so (nearly) all 64 slots of a warp evaluate every trip.  A march
+// depends only on its own ray, so the order in which slots pick up work cannot change any output bit.
+// The per-ray traffic is the algorithmic minimum: read float4 o+time, float4 d+closest (32 B), write
+// t + key (8 B) when this SDF is the new closest hit.
+// ------------------------------------------------------------------------------------------
+#define EXT_T 128
+template <int V>
+__global__ void __launch_bounds__(EXT_T, 8) k_extend_march(const __grid_constant__ DevScene sc, const PassBufs pb, const Thr thr,
+                                                          const int hk, const int* __restrict__ batch_prefix, int* __restrict__ work_ctr) {
+  const SdfK k = make_sdfk(sc.hit[hk], sc.one);  // fractal constants: kernel-parameter bank -> registers, once
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   const float S = sc.rc.sdf_detail_scale;
   const float c0 = 0.00005f * S, c1 = 0.05f * S;
   const int max_marches = sc.rc.max_marches;
   const int n_batches = batch_prefix[pb.n_tiles];
-  bool have = false, first = false, exhausted = false;
-  f3 o = {0, 0, 0}, d = {0, 0, 0};
-  float closest = 0.0f, t = 0.0f;
-  int steps = 0, evals = 0;
-  size_t q = 0, g = 0;
-  int cur_ts = 0, cur_pos = 0, cur_end = 0;
-  SdfEval ev;
-  ev.w = ev.c = mk3(0, 0, 0);
-  ev.dr = ev.m = 0.0f;
-  ev.it = 0;
+  bool have0 = false, have1 = false, first0 = false, first1 = false, exhausted = false;
+  float2 ox = splat2(0.0f), oy = ox, oz = ox, dx = ox, dy = ox, dz = ox, t = ox, closest = ox;
+  int q0 = 0, q1 = 0, g0 = 0, g1 = 0, steps0 = 0, steps1 = 0, evals = 0, bulb_iters = 0;
+  int cur_base = 0, cur_pos = 0, cur_end = 0;
   while (true) {
     __syncwarp();
-    unsigned idle = __ballot_sync(0xffffffffu, !have);
-    while (idle && !(exhausted && cur_pos >= cur_end)) {
+    unsigned idle0 = __ballot_sync(0xffffffffu, !have0), idle1 = __ballot_sync(0xffffffffu, !have1);
+    while ((idle0 | idle1) && !(exhausted && cur_pos >= cur_end)) {
       if (cur_pos >= cur_end) {
         int b = 0;
         if (lane == 0) b = atomicAdd(work_ctr, 1);
@@ -618,349 +339,124 @@ __global__ void __launch_bounds__(EXT_T, 10) k_extend_march(const __grid_constan
           const int mid = (lo + hi) >> 1;
           if (__ldg(batch_prefix + mid) <= b) lo = mid; else hi = mid;
         }
-        cur_ts = lo;
+        cur_base = lo * pb.R;
         cur_pos = (b - __ldg(batch_prefix + lo)) * EXT_BATCH;
         cur_end = min(cur_pos + EXT_BATCH, pb.n_live[lo]);
       }
       const int avail = cur_end - cur_pos;
-      const int rank = __popc(idle & lt);
-      if (!have && rank < avail) {
-        q = (size_t)cur_ts * pb.R + cur_pos + rank;
-        g = (size_t)cur_ts * pb.R + pb.q_live[q];
-        const float4 o4 = pb.o_time[g], d4 = pb.d_t[g];
-        o = mk3(o4.x, o4.y, o4.z);
-        d = mk3(d4.x, d4.y, d4.z);
-        closest = d4.w;
-        first = true;
-        have = true;
-        if (FLAT) eval_start(ev, s_h, o);
+      const int n0 = __popc(idle0);
+      const int rank0 = __popc(idle0 & lt), rank1 = n0 + __popc(idle1 & lt);
+      if (!have0 && rank0 < avail) {
+        q0 = cur_base + cur_pos + rank0;
+        g0 = cur_base + pb.q_live[q0];
+        const float4 o4 = pb.o_time[g0], d4 = pb.d_t[g0];
+        ox.x = o4.x, oy.x = o4.y, oz.x = o4.z, dx.x = d4.x, dy.x = d4.y, dz.x = d4.z, closest.x = d4.w;
+        first0 = have0 = true;
       }
-      cur_pos += min(avail, __popc(idle));
-      idle = __ballot_sync(0xffffffffu, !have);
+      if (!have1 && rank1 < avail) {
+        q1 = cur_base + cur_pos + rank1;
+        g1 = cur_base + pb.q_live[q1];
+        const float4 o4 = pb.o_time[g1], d4 = pb.d_t[g1];
+        ox.y = o4.x, oy.y = o4.y, oz.y = o4.z, dx.y = d4.x, dy.y = d4.y, dz.y = d4.z, closest.y = d4.w;
+        first1 = have1 = true;
+      }
+      cur_pos += min(avail, n0 + __popc(idle1));
+      idle0 = __ballot_sync(0xffffffffu, !have0), idle1 = __ballot_sync(0xffffffffu, !have1);
     }
-    if (!__any_sync(0xffffffffu, have)) break;
-    if (have) {
-      float dd = 0.0f;
-      bool ready = true;
-      if (FLAT) {
-        if (eval_more(ev, s_h)) eval_step(ev, s_h);
-        ready = !eval_more(ev, s_h);
-        if (ready) dd = eval_finish(ev, s_h);
+    if (!__any_sync(0xffffffffu, have0 || have1)) break;
+    // evaluation point of each slot: the origin for the first evaluation (sdf.rs:60), ray.point_at(t) afterwards
+    // (ray.rs:22-24: dir.mul_add(t, origin)); an empty slot evaluates a far point (cheapest for every estimator)
+    float2 px = muladd2(dx, t, ox, k.one), py = muladd2(dy, t, oy, k.one), pz = muladd2(dz, t, oz, k.one);
+    if (first0) px.x = ox.x, py.x = oy.x, pz.x = oz.x;
+    if (first1) px.y = ox.y, py.y = oy.y, pz.y = oz.y;
+    if (!have0) px.x = 100.0f, py.x = 0.0f, pz.x = 0.0f;
+    if (!have1) px.y = 100.0f, py.y = 0.0f, pz.y = 0.0f;
+    const float2 dd = sdf_dist2<V>(k, px, py, pz, bulb_iters);
+    if (have0) {
+      ++evals;
+      bool end;
+      if (first0) {
+        t.x = dd.x, steps0 = 0, first0 = false;
+        end = t.x != t.x;  // NaN start: returns NaN, the caller's t < closest is false (hitable.rs:190)
       } else {
-        dd = sdf_dist(s_h, first ? o : fma3s(d, t, o));
-      }
-      if (ready) {
-        ++evals;
-        bool end = false;
-        if (first) {
-          t = dd;
-          steps = 0;
-          first = false;
-          end = t != t;
+        const bool hit = dm::abs(dd.x) < dm::max(c0, c1 * thr.at(t.x));
+        if (hit || t.x > closest.x) {
+          end = true;
         } else {
-          const bool hit = dm::abs(dd) < dm::max(c0, c1 * thr.at(t));
-          const bool gt = t > closest;
-          if (hit || gt) {
-            end = true;
-          } else {
-            t = t + dd;
-            ++steps;
-            end = (t != t) || steps >= max_marches;
-          }
+          t.x = t.x + dd.x;
+          ++steps0;
+          end = (t.x != t.x) || steps0 >= max_marches;  // a NaN can never satisfy hit/gt again: marches to exhaustion, returns NaN
         }
-        if (end) {
-          if (t < closest) {  // hitable.rs:190-193
-            pb.d_t[g].w = t;
-            pb.q_key[q] = hk;
-          }
-          have = false;
-        } else if (FLAT) {
-          eval_start(ev, s_h, fma3s(d, t, o));
+      }
+      if (end) {
+        if (t.x < closest.x) {  // hitable.rs:190-193
+          pb.d_t[g0].w = t.x;
+          pb.q_key[q0] = hk;
         }
+        have0 = false;
+      }
+    }
+    if (have1) {
+      ++evals;
+      bool end;
+      if (first1) {
+        t.y = dd.y, steps1 = 0, first1 = false;
+        end = t.y != t.y;
+      } else {
+        const bool hit = dm::abs(dd.y) < dm::max(c0, c1 * thr.at(t.y));
+        if (hit || t.y > closest.y) {
+          end = true;
+        } else {
+          t.y = t.y + dd.y;
+          ++steps1;
+          end = (t.y != t.y) || steps1 >= max_marches;
+        }
+      }
+      if (end) {
+        if (t.y < closest.y) {
+          pb.d_t[g1].w = t.y;
+          pb.q_key[q1] = hk;
+        }
+        have1 = false;
       }
     }
   }
   warp_add(pb.counters + CNT_EVALS_EXTEND, evals);
+  if (V == SDFV_BULB) warp_add(pb.counters + CNT_BULB_ITERS_EXTEND, bulb_iters);
 }
 
-// ---- K4/K5 v2: shade with a block-level shadow-segment pool ------------------------------------
-// Per round (surface NEE, then each volume march) every lane prepares its 4 light samples and
-// pushes the shadow segments that still need a sphere-march into a shared-memory pool; all
-// warps of the block then march the pool with lane refill; then each lane folds the
-// visibilities into its radiance in the reference's order.  Two exact pre-filters:
-//  * a segment whose unoccluded contribution c is all (+-0 | NaN) is not marched: c*0 and c*1
-//    are the same bits, so visibility cannot change the result (back-facing lights);
-//  * analytic spheres are tested first; product of {0,1} factors (hitable.rs:164-168).
-#define SH_T 128
-#define SH_POOL (SH_T * 4)
-#define SH_MAX_SDF 4
-struct ShadeSmem {
-  RaynHitable hit[RAYN_MAX_HITABLES];
-  RaynMaterial mat[RAYN_MAX_MATERIALS];
-  RaynLight light[RAYN_MAX_LIGHTS];
-  float vis[SH_POOL];
-  float cx[4][SH_T], cy[4][SH_T], cz[4][SH_T], cden[4][SH_T], ctr[4][SH_T];
-  int n, next;
-  int pad_[2];
-  // followed by float4 pa[pool_cap] (start.xyz, max_dist) and float4 pb[pool_cap] (dir.xyz, bits(owner | hidx << 16)),
-  // pool_cap = SH_POOL * number of SDF hitables
-};
-static_assert(sizeof(ShadeSmem) % 16 == 0, "pool must stay float4 aligned");
-static inline size_t shade_smem_bytes(int n_sdf) { return sizeof(ShadeSmem) + (size_t)2 * SH_POOL * (n_sdf > 0 ? n_sdf : 1) * sizeof(float4); }
-
-__global__ void __launch_bounds__(SH_T, 4) k_shade2(const __grid_constant__ DevScene sc, const DevFrame fr, const PassBufs pb,
-                                                    const int depth, const Thr thr, const int pool_cap) {
-  extern __shared__ __align__(16) unsigned char sh_raw[];
-  ShadeSmem& sm = *reinterpret_cast<ShadeSmem*>(sh_raw);
-  float4* __restrict__ s_pa = reinterpret_cast<float4*>(sh_raw + sizeof(ShadeSmem));
-  float4* __restrict__ s_pb = s_pa + pool_cap;
-  const int ts = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
-  const int s = blockIdx.x * SH_T + tid;
-  const int nslots = pb.n_slots[ts];
-  if (blockIdx.x * SH_T >= nslots) return;  // block-uniform
-  for (int k = tid; k < sc.n_hit; k += SH_T) sm.hit[k] = sc.hit[k];
-  for (int k = tid; k < sc.n_mat; k += SH_T) sm.mat[k] = sc.mat[k];
-  for (int k = tid; k < sc.n_lights; k += SH_T) sm.light[k] = sc.light[k];
-  int* __restrict__ qs = pb.q_shade + (size_t)ts * pb.QS;
-  const int id = s < nslots ? qs[s] : -1;
-  const bool valid = id >= 0;
-  const TileGeom tg = tile_geom(fr, pb.tile_ids[ts]);
-  int sample = 0;
-  float scramble = 0.0f;
-  if (valid) {
-    const int pl = id / fr.spp;
-    sample = id - pl * fr.spp;
-    const int xl = pl / tg.th, yl = pl - xl * tg.th;
-    scramble = __ldg(fr.scramble + (tg.x0 + xl) + (size_t)(tg.y0 + yl) * fr.W);
-  }
-  const int n1 = 3 + fr.vm, n2h = (12 + 8 * fr.vm) / 2;
-  const int set1 = 1 + depth * n1, set2 = 2 + depth * n2h;
-  const int nl = sc.n_lights;
-  unsigned pack = 0;
-  if (nl > 0)
-    pack = (unsigned)light_index(samp1(fr, sample, scramble, set1 + 0), nl) | ((unsigned)light_index(samp1(fr, sample, scramble, set1 + 1), nl) << 8) |
-           ((unsigned)light_index(samp1(fr, sample, scramble, set1 + 2), nl) << 16);
-  // w[r] = the 4 light indices of round r, one byte per packet lane (integrator.rs:76-77,100-102)
-  unsigned w0 = 0, w1 = 0, w2 = 0;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const unsigned pk = __shfl_sync(0xffffffffu, pack, (lane & ~3) + k);
-    w0 |= (pk & 0xffu) << (8 * k);
-    w1 |= ((pk >> 8) & 0xffu) << (8 * k);
-    w2 |= ((pk >> 16) & 0xffu) << (8 * k);
-  }
-  __syncthreads();  // staged constants visible
-
-  int evals = 0, shadows = 0;
-  ShadingPoint sp;
-  f3 radiance = {0, 0, 0}, throughput = {0, 0, 0}, wo = {0, 0, 0};
-  float vt = 1.0f;
-  bool recv = false;
-  int mat_idx = 0;
-  size_t g = 0;
-  const bool has_ext = sc.vol.has_extinction != 0;
-  const float neg_rho_t = -sc.vol.coeff_extinction;
-  if (valid) {
-    const int* __restrict__ bs = pb.bin_start + ts * (RAYN_MAX_HITABLES + 1);
-    int obj = 0;
-    while (obj + 1 < sc.n_hit && s >= bs[obj + 1]) ++obj;
-    const RaynHitable& h = sm.hit[obj];
-    mat_idx = h.material;
-    g = (size_t)ts * pb.R + id;
-    const float4 o4 = pb.o_time[g], d4 = pb.d_t[g], r4 = pb.rad[g], t4 = pb.thr[g];
-    sp.o = mk3(o4.x, o4.y, o4.z);
-    sp.d = mk3(d4.x, d4.y, d4.z);
-    sp.time = o4.w;
-    sp.t = d4.w;
-    shading_info(sc, h, thr, sp, &evals);
-    radiance = mk3(r4.x, r4.y, r4.z);
-    throughput = mk3(t4.x, t4.y, t4.z);
-    wo = -sp.d;
-    vt = has_ext ? dm::exp(neg_rho_t * sp.t) : 1.0f;            // integrator.rs:64-68
-    radiance = radiance + bsdf_le(sm.mat[mat_idx], wo) * throughput * vt;  // :70-71
-    recv = receives_light(sm.mat[mat_idx]);
-  }
-  warp_add(pb.counters + CNT_SHADE_LANES, valid ? 1 : 0);
-
-  const bool scat = sc.vol.has_scattering != 0 && nl > 0;
-  const int n_rounds = nl > 0 ? 1 + (scat ? fr.vm : 0) : 0;
-  const float S = sc.rc.sdf_detail_scale;
-  const float oc0 = 0.0001f * S, oc1 = 0.00001f * S;
-  const int max_vis = sc.rc.max_vis_marches;
-  for (int round = 0; round < n_rounds; ++round) {
-    if (tid == 0) {
-      sm.n = 0;
-      sm.next = 0;
-    }
-    __syncthreads();
-    const bool act = valid && (round == 0 ? recv : true);
-    const unsigned wr = round == 0 ? w0 : (round == 1 ? w1 : w2);
-    if (act) {
-      const float vol_sample = round == 0 ? 0.0f : samp1(fr, sample, scramble, set1 + 1);  // samples_1d[1], :115
-#pragma unroll 1
-      for (int i = 0; i < 4; ++i) {
-        const int li_idx = (int)((wr >> (8 * i)) & 0xffu);
-        const RaynLight& L = sm.light[li_idx];
-        const int set = round == 0 ? set2 + i : set2 + 4 + 4 * (round - 1) + i;
-        const float u0 = samp2(fr, 0, sample, scramble, set), u1 = samp2(fr, 1, sample, scramble, set);
-        f3 start, end_point, li, c;
-        float den, trans = 1.0f;
-        if (round == 0) {  // surface_sample_one_light :207-240
-          float pdf;
-          light_sample(L, u0, u1, sp.point, &end_point, &li, &pdf);
-          f3 wi = end_point - sp.point;
-          const float dist = mag(wi);
-          wi = wi / dist;
-          start = sp.point + sp.normal * dm::signum(dot(sp.normal, wi)) * sp.offset_by;
-          const f3 f = bsdf_f(sm.mat[mat_idx], wo, wi, sp.normal) * dm::max(dot(sp.normal, wi), 0.0f);
-          const float tr = has_ext ? dm::exp(neg_rho_t * dist) : 1.0f;
-          c = li * f * tr;
-          den = pdf;
-        } else {  // volume_sample_one_light :242-281
-          float vol_dist, vol_pdf, light_pdf;
-          light_sample_volume(L, vol_sample, sp.o, sp.d, sp.t, &vol_dist, &vol_pdf);
-          start = sp.o + sp.d * vol_dist;
-          light_sample(L, u0, u1, start, &end_point, &li, &light_pdf);
-          const float dist_point_to_light = mag(end_point - start);
-          const float f = 1.0f / (4.0f * RT_PI);
-          const float tr = has_ext ? dm::exp(neg_rho_t * dist_point_to_light) : 1.0f;
-          c = li * f * tr;
-          den = vol_pdf * light_pdf;
-          trans = has_ext ? dm::exp(neg_rho_t * vol_dist) : 1.0f;  // :122-126
-        }
-        sm.cx[i][tid] = c.x, sm.cy[i][tid] = c.y, sm.cz[i][tid] = c.z, sm.cden[i][tid] = den, sm.ctr[i][tid] = trans;
-        ++shadows;
-        float vis = 1.0f;
-        const bool irrelevant = (c.x == 0.0f || c.x != c.x) && (c.y == 0.0f || c.y != c.y) && (c.z == 0.0f || c.z != c.z);
-        if (!irrelevant) {
-          for (int k = 0; k < sc.n_hit && vis != 0.0f; ++k)
-            if (sm.hit[k].kind == RAYN_HITABLE_SPHERE) vis = sphere_occluded(sm.hit[k], start, end_point, 0.0f);
-          if (vis != 0.0f) {
-            f3 dir = end_point - start;  // TracedSDF::occluded prologue, sdf.rs:26-28
-            const float max_dist = mag(dir);
-            dir = dir / max_dist;
-            for (int k = 0; k < sc.n_hit; ++k)
-              if (sm.hit[k].kind != RAYN_HITABLE_SPHERE) {
-                const int slot = atomicAdd(&sm.n, 1);
-                s_pa[slot] = make_float4(start.x, start.y, start.z, max_dist);
-                s_pb[slot] = make_float4(dir.x, dir.y, dir.z, __int_as_float((tid * 4 + i) | (k << 16)));
-              }
-          }
-        }
-        sm.vis[tid * 4 + i] = vis;
-      }
-    }
-    __syncthreads();
-    {  // ---- cooperative sphere-march of the pool: TracedSDF::occluded, sdf.rs:25-57 / SURVEY §9.2
-      const int pool_n = sm.n;
-      const unsigned lt = (1u << lane) - 1u;
-      bool have = false, first = false, exhausted = false;
-      f3 st = {0, 0, 0}, dir = {0, 0, 0};
-      float max_dist = 0.0f, t = 0.0f;
-      int owner = 0, hk = 0, steps = 0;
-      while (true) {
-        __syncwarp();
-        const unsigned idle = __ballot_sync(0xffffffffu, !have);
-        if (idle && !exhausted) {
-          int base = 0;
-          if (lane == 0) base = atomicAdd(&sm.next, __popc(idle));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          const int idx = base + __popc(idle & lt);
-          if (base + __popc(idle) >= pool_n) exhausted = true;
-          if (!have && idx < pool_n) {
-            const float4 a = s_pa[idx], b = s_pb[idx];
-            st = mk3(a.x, a.y, a.z);
-            max_dist = a.w;
-            dir = mk3(b.x, b.y, b.z);
-            const int ow = __float_as_int(b.w);
-            owner = ow & 0xffff;
-            hk = ow >> 16;
-            first = true;
-            have = true;
-          }
-        }
-        if (!__any_sync(0xffffffffu, have)) break;
-        if (have) {
-          const f3 p = first ? st : fma3s(dir, t, st);
-          const float dd = sdf_dist(sm.hit[hk], p);
-          ++evals;
-          bool done = false;
-          if (first) {
-            t = dd;
-            first = false;
-            steps = 0;
-            done = (t != t) || (t > max_dist);
-          } else if (dm::abs(dd) < dm::max(oc0, oc1 * t)) {
-            sm.vis[owner] = 0.0f;  // occluded (only ever written as 0: product semantics)
-            done = true;
-          } else {
-            t = t + dd;
-            ++steps;
-            done = (t != t) || steps >= max_vis || (t > max_dist);
-          }
-          if (done) have = false;
-        }
-      }
-    }
-    __syncthreads();
-    if (act) {
-      if (round == 0) {
-        const float correction = (float)nl / 4.0f;  // :79-80
-#pragma unroll 1
-        for (int i = 0; i < 4; ++i) {
-          const f3 contrib = mk3(sm.cx[i][tid], sm.cy[i][tid], sm.cz[i][tid]) * sm.vis[tid * 4 + i] / sm.cden[i][tid];
-          radiance = radiance + contrib * throughput * correction * vt;  // :91-92
-        }
-      } else {
-        const float rho_s = sc.vol.coeff_scattering;
-        const float correction = (float)nl / 4.0f / (float)fr.vm;  // :104-108
-#pragma unroll 1
-        for (int i = 0; i < 4; ++i) {
-          const f3 contrib = mk3(sm.cx[i][tid], sm.cy[i][tid], sm.cz[i][tid]) * sm.vis[tid * 4 + i] / sm.cden[i][tid];
-          radiance = radiance + contrib * throughput * correction * rho_s * sm.ctr[i][tid];  // :128-129
-        }
-      }
-    }
-  }
-
-  if (valid) {
-    const RaynMaterial& mat = sm.mat[mat_idx];
-    if (recv) {  // :134-188
-      const int setb = set2 + 4 + 4 * fr.vm;
-      const Scatter se = bsdf_scatter(mat, wo, sp, samp1(fr, sample, scramble, set1 + 3), samp2(fr, 0, sample, scramble, setb),
-                                      samp2(fr, 1, sample, scramble, setb), samp2(fr, 0, sample, scramble, setb + 1),
-                                      samp2(fr, 1, sample, scramble, setb + 1));
-      const float ndl = dm::abs(dot(se.wi, sp.normal));
-      f3 new_throughput = throughput * vt * se.f * ndl / se.pdf;
-      float roulette_factor = 0.0f;
-      if (depth > 2) {
-        roulette_factor = dm::max(1.0f - component_max(throughput), 0.05f);
-        new_throughput = new_throughput / (1.0f - roulette_factor);
-      }
-      if (depth == 0) pb.nrm0[g] = make_float4(sp.normal.x, sp.normal.y, sp.normal.z, __uint_as_float((unsigned)s + 1u));
-      const float roulette_sample = samp1(fr, sample, scramble, set1 + 4);
-      if (depth >= fr.max_bounces || roulette_sample < roulette_factor) {
-        pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
-        pb.term[g] = (TERM_COLOR << 30) | ((unsigned)depth << 20) | (unsigned)s;
-        qs[s] = -1;
-      } else {
-        const f3 no = sp.point + sp.normal * dm::signum(dot(sp.normal, se.wi)) * sp.offset_by;
-        if (!any_nan(new_throughput)) throughput = new_throughput;
-        pb.o_time[g] = make_float4(no.x, no.y, no.z, sp.time);
-        pb.d_t[g] = make_float4(se.wi.x, se.wi.y, se.wi.z, 0.0f);
-        pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
-        pb.thr[g] = make_float4(throughput.x, throughput.y, throughput.z, 0.0f);
-      }
-    } else {  // :189-203
-      pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
-      pb.term[g] = ((depth == 0 ? TERM_BACKGROUND : TERM_COLOR) << 30) | ((unsigned)depth << 20) | (unsigned)s;
-      qs[s] = -1;
-    }
-  }
-  warp_add(pb.counters + CNT_EVALS_SHADOW, evals);
-  warp_add(pb.counters + CNT_SHADOW_RAYS, shadows);
+// ------------------------------------------------------------------------------------------
+// K3b normals: TracedSDF::get_shading_info (sdf.rs:85-101) for the shading slots of SDF hitable `hk`:
+// sdfu's tetrahedral normals_fast (oracle/README.md A8) = 4 distance evaluations = 2 packed evaluations
+// per lane, specialised on the SDF like the march kernels.  Writes nrm[g] = (normal, offset_by).
+// ------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(128, 8) k_normals(const __grid_constant__ DevScene sc, const PassBufs pb, const Thr thr, const int hk) {
+  const int ts = blockIdx.y;
+  const int* __restrict__ bs = pb.bin_start + ts * (RAYN_MAX_HITABLES + 1);
+  const int s0 = bs[hk], s1 = bs[hk + 1];
+  const int s = s0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= s1) return;
+  const int id = pb.q_shade[(size_t)ts * pb.QS + s];
+  if (id < 0) return;  // padding lane (hitable.rs:100-111)
+  const SdfK k = make_sdfk(sc.hit[hk], sc.one);
+  const size_t g = (size_t)ts * pb.R + id;
+  const float4 o4 = pb.o_time[g], d4 = pb.d_t[g];
+  const f3 point = fma3s(mk3(d4.x, d4.y, d4.z), d4.w, mk3(o4.x, o4.y, o4.z));  // WHit::point -> ray.point_at, ray.rs:22-24
+  const float eps = dm::max(0.0001f, sc.rc.sdf_detail_scale * thr.at(d4.w));
+  // tetrahedron offsets k0 = (1,-1,-1), k1 = (-1,-1,1), k2 = (-1,1,-1), k3 = (1,1,1); n = ((k0 d0 + k1 d1) + k2 d2) + k3 d3
+  int it = 0;
+  const float ex = 1.0f * eps, en = -1.0f * eps;
+  const float2 da = sdf_dist2<V>(k, f2(point.x + ex, point.x + en), f2(point.y + en, point.y + en), f2(point.z + en, point.z + ex), it);
+  const float2 db = sdf_dist2<V>(k, f2(point.x + en, point.x + ex), f2(point.y + ex, point.y + ex), f2(point.z + en, point.z + ex), it);
+  f3 n = mk3(1.0f, -1.0f, -1.0f) * da.x;
+  n = n + mk3(-1.0f, -1.0f, 1.0f) * da.y;
+  n = n + mk3(-1.0f, 1.0f, -1.0f) * db.x;
+  n = n + mk3(1.0f, 1.0f, 1.0f) * db.y;
+  n = normalized(n);
+  pb.nrm[g] = make_float4(n.x, n.y, n.z, eps);
+  warp_add_partial(pb.counters + CNT_EVALS_NORMALS, 4);
 }
-
 // ==========================================================================================
 // v3 shading: k_shade_pre -> k_shadow (persistent) -> k_shade_post.
 // The block-level pool of k_shade2 still drains to a tail every round; v3 pushes the shadow
@@ -1059,7 +555,7 @@ __global__ void __launch_bounds__(128, 8) k_shade_pre(const __grid_constant__ De
   const SlotCtx cx = slot_ctx(sc, fr, pb, ts, s, nslots, depth, threadIdx.x & 31);
   const bool valid = cx.id >= 0;
   warp_add(pb.counters + CNT_SHADE_LANES, valid ? 1 : 0);
-  int evals = 0, shadows = 0;
+  int shadows = 0;
   const size_t g = (size_t)ts * pb.R + (valid ? cx.id : 0);
   float4 o4 = make_float4(0, 0, 0, 0);
   if (valid) o4 = pb.o_time[g];
@@ -1083,158 +579,171 @@ __global__ void __launch_bounds__(128, 8) k_shade_pre(const __grid_constant__ De
     const bool has_ext = sc.vol.has_extinction != 0;
     const float neg_rho_t = -sc.vol.coeff_extinction;
     const float vt = has_ext ? dm::exp(neg_rho_t * sp.t) : 1.0f;  // integrator.rs:64-68
+    const f3 radiance = mk3(r4.x, r4.y, r4.z) + bsdf_le(mat, wo) * mk3(t4.x, t4.y, t4.z) * vt;  // :70-71
+    pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
     if (!recv && !scat) {
       // Sky / Emissive without volumetrics: emission is the whole shading step (integrator.rs:70-71,
       // 189-203); the path ends here.  Every lane of its packet has the same material, so nobody needs
       // this lane's light choice and k_shade_post can treat the slot as empty.
-      const f3 radiance = mk3(r4.x, r4.y, r4.z) + bsdf_le(mat, wo) * mk3(t4.x, t4.y, t4.z) * vt;
-      pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
-      pb.term[g] = ((depth == 0 ? TERM_BACKGROUND : TERM_COLOR) << 30) | ((unsigned)depth << 20) | (unsigned)s;
+      pb.term[g] = ((depth == 0 ? TERM_BACKGROUND : TERM_COLOR) << 30) | ((unsigned)depth << TERM_DEPTH_SHIFT) | (unsigned)s;
       pb.q_shade[(size_t)ts * pb.QS + s] = -1;
     } else {
-    shading_info(sc, h, thr, sp, &evals, false, time0);
-    pb.nrm[g] = make_float4(sp.normal.x, sp.normal.y, sp.normal.z, sp.offset_by);
-    const f3 radiance = mk3(r4.x, r4.y, r4.z) + bsdf_le(mat, wo) * mk3(t4.x, t4.y, t4.z) * vt;  // :70-71
-    pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
-    unsigned vis = 0xffffffffu;
-    for (int round = (recv ? 0 : 1); round < n_rounds; ++round) {
-      const unsigned wr = round == 0 ? cx.w0 : (round == 1 ? cx.w1 : cx.w2);
-      const float vol_sample = round == 0 ? 0.0f : samp1(fr, cx.sample, cx.scramble, cx.set1 + 1);  // samples_1d[1], :115
-#pragma unroll 1
-      for (int i = 0; i < 4; ++i) {
-        const int set = round == 0 ? cx.set2 + i : cx.set2 + 4 + 4 * (round - 1) + i;
-        const LightContrib lc = light_contrib(sc.light[(wr >> (8 * i)) & 0xffu], mat, sp, wo, round, samp2(fr, 0, cx.sample, cx.scramble, set),
-                                              samp2(fr, 1, cx.sample, cx.scramble, set), vol_sample, has_ext, neg_rho_t);
-        ++shadows;
-        const int bit = round * 4 + i;
-        pb.lc_c[g * pb.lc_ns + bit] = make_float4(lc.c.x, lc.c.y, lc.c.z, lc.den);  // k_shade_post folds these in; HBM is idle, ALU is not
-        if (round > 0) pb.lc_t[g * 8 + (bit - 4)] = lc.trans;
-        // a contribution that is (+-0 | NaN) in every channel is the same bits for visibility 0 and 1
-        const bool irrelevant = (lc.c.x == 0.0f || lc.c.x != lc.c.x) && (lc.c.y == 0.0f || lc.c.y != lc.c.y) && (lc.c.z == 0.0f || lc.c.z != lc.c.z);
-        if (irrelevant) continue;
-        float v = 1.0f;  // analytic spheres first: product of {0,1} factors (hitable.rs:164-168)
-        for (int k = 0; k < sc.n_hit && v != 0.0f; ++k)
-          if (sc.hit[k].kind == RAYN_HITABLE_SPHERE) v = sphere_occluded(sc.hit[k], lc.start, lc.end_point, time0);
-        if (v == 0.0f) {
-          vis &= ~(1u << bit);
-          continue;
-        }
-        f3 dir = lc.end_point - lc.start;  // TracedSDF::occluded prologue, sdf.rs:26-28
-        const float max_dist = mag(dir);
-        dir = dir / max_dist;
-        for (int k = 0; k < sc.n_hit; ++k)
-          if (sc.hit[k].kind != RAYN_HITABLE_SPHERE) {
-            const unsigned am = __activemask();  // opportunistic warp aggregation of the queue append
-            const int leader = __ffs(am) - 1, ln = threadIdx.x & 31;
-            int base = 0;
-            if (ln == leader) base = atomicAdd(pb.seg_count, __popc(am));
-            base = __shfl_sync(am, base, leader);
-            const int slot = base + __popc(am & ((1u << ln) - 1u));
-            pb.seg_a[slot] = make_float4(lc.start.x, lc.start.y, lc.start.z, max_dist);
-            pb.seg_b[slot] = make_float4(dir.x, dir.y, dir.z, __int_as_float(bit | (k << 8)));
-            pb.seg_owner[slot] = (int)g;
-          }
+      sp.point = fma3s(sp.d, sp.t, sp.o);  // WHit::point -> ray.point_at, ray.rs:22-24
+      if (h.kind == RAYN_HITABLE_SPHERE) {  // sphere.rs:74-86
+        sp.normal = normalized(sp.point - sphere_center(h, time0));
+        sp.offset_by = 0.0f;
+        pb.nrm[g] = make_float4(sp.normal.x, sp.normal.y, sp.normal.z, 0.0f);
+      } else {  // sdf.rs:85-101: written by k_normals<V> for this hitable
+        const float4 n4 = pb.nrm[g];
+        sp.normal = mk3(n4.x, n4.y, n4.z);
+        sp.offset_by = n4.w;
       }
-    }
-    pb.vis[g] = vis;
+      unsigned vis = 0xffffffffu;
+      for (int round = (recv ? 0 : 1); round < n_rounds; ++round) {
+        const unsigned wr = round == 0 ? cx.w0 : (round == 1 ? cx.w1 : cx.w2);
+        const float vol_sample = round == 0 ? 0.0f : samp1(fr, cx.sample, cx.scramble, cx.set1 + 1);  // samples_1d[1], :115
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) {
+          const int set = round == 0 ? cx.set2 + i : cx.set2 + 4 + 4 * (round - 1) + i;
+          const LightContrib lc = light_contrib(sc.light[(wr >> (8 * i)) & 0xffu], mat, sp, wo, round, samp2(fr, 0, cx.sample, cx.scramble, set),
+                                                samp2(fr, 1, cx.sample, cx.scramble, set), vol_sample, has_ext, neg_rho_t);
+          ++shadows;
+          const int bit = round * 4 + i;
+          pb.lc_c[g * pb.lc_ns + bit] = make_float4(lc.c.x, lc.c.y, lc.c.z, lc.den);  // k_shade_post folds these in; HBM is idle, ALU is not
+          if (round > 0) pb.lc_t[g * 8 + (bit - 4)] = lc.trans;
+          // a contribution that is (+-0 | NaN) in every channel is the same bits for visibility 0 and 1
+          const bool irrelevant = (lc.c.x == 0.0f || lc.c.x != lc.c.x) && (lc.c.y == 0.0f || lc.c.y != lc.c.y) && (lc.c.z == 0.0f || lc.c.z != lc.c.z);
+          if (irrelevant) continue;
+          float v = 1.0f;  // analytic spheres first: product of {0,1} factors (hitable.rs:164-168)
+          for (int k = 0; k < sc.n_hit && v != 0.0f; ++k)
+            if (sc.hit[k].kind == RAYN_HITABLE_SPHERE) v = sphere_occluded(sc.hit[k], lc.start, lc.end_point, time0);
+          if (v == 0.0f) {
+            vis &= ~(1u << bit);
+            continue;
+          }
+          f3 dir = lc.end_point - lc.start;  // TracedSDF::occluded prologue, sdf.rs:26-28
+          const float max_dist = mag(dir);
+          dir = dir / max_dist;
+          int j = 0;  // SDF ordinal
+          for (int k = 0; k < sc.n_hit; ++k)
+            if (sc.hit[k].kind != RAYN_HITABLE_SPHERE) {
+              const unsigned am = __activemask();  // opportunistic warp aggregation of the queue append
+              const int leader = __ffs(am) - 1, ln = threadIdx.x & 31;
+              int base = 0;
+              if (ln == leader) base = atomicAdd(pb.seg_count + j, __popc(am));
+              base = __shfl_sync(am, base, leader);
+              const size_t slot = (size_t)j * pb.seg_cap + base + __popc(am & ((1u << ln) - 1u));
+              pb.seg_a[slot] = make_float4(lc.start.x, lc.start.y, lc.start.z, max_dist);
+              pb.seg_b[slot] = make_float4(dir.x, dir.y, dir.z, __int_as_float((int)(((unsigned)g << 4) | (unsigned)bit)));
+              ++j;
+            }
+        }
+      }
+      pb.vis[g] = vis;
     }
   }
-  warp_add(pb.counters + CNT_EVALS_SHADOW, evals);
   warp_add(pb.counters + CNT_SHADOW_RAYS, shadows);
 }
 
-// K5: persistent shadow sphere-march over the pass-wide segment queue.
-// TracedSDF::occluded per lane (sdf.rs:25-57); occlusion clears the owner's bit.
+// ------------------------------------------------------------------------------------------
+// K5 shadow sphere-march: TracedSDF::occluded per slot (sdf.rs:25-57) over the segment
+// queue of SDF ordinal `j` (hitable index `hk`); occlusion clears the owner's visibility bit.  Same
+// persistent, two-slots-per-thread, packed-f32x2 structure as k_extend_march.  Traffic per segment:
+// 32 B read (+ 4 B atomic when occluded).
+// ------------------------------------------------------------------------------------------
 #define SHD_T 128
-template <bool FLAT>
-__global__ void __launch_bounds__(SHD_T, 10) k_shadow(const __grid_constant__ DevScene sc, const PassBufs pb, int* __restrict__ work_ctr) {
-  __shared__ RaynHitable s_hit[RAYN_MAX_HITABLES];
-  for (int k = threadIdx.x; k < sc.n_hit; k += SHD_T) s_hit[k] = sc.hit[k];
-  __syncthreads();
+#define SHD_BATCH 128
+template <int V>
+__global__ void __launch_bounds__(SHD_T, 8) k_shadow(const __grid_constant__ DevScene sc, const PassBufs pb, const int hk, const int j,
+                                                    int* __restrict__ work_ctr) {
+  const SdfK k = make_sdfk(sc.hit[hk], sc.one);
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
-  const int n_seg = *pb.seg_count;
+  const int n_seg = pb.seg_count[j];
+  const float4* __restrict__ seg_a = pb.seg_a + (size_t)j * pb.seg_cap;
+  const float4* __restrict__ seg_b = pb.seg_b + (size_t)j * pb.seg_cap;
   const float S = sc.rc.sdf_detail_scale;
   const float oc0 = 0.0001f * S, oc1 = 0.00001f * S;
   const int max_vis = sc.rc.max_vis_marches;
-  bool have = false, first = false, exhausted = false;
-  f3 st = {0, 0, 0}, dir = {0, 0, 0};
-  float max_dist = 0.0f, t = 0.0f;
-  int owner = 0, bit = 0, hk = 0, steps = 0, evals = 0;
+  bool have0 = false, have1 = false, first0 = false, first1 = false, exhausted = false;
+  float2 sx = splat2(0.0f), sy = sx, sz = sx, dx = sx, dy = sx, dz = sx, t = sx, max_dist = sx;
+  int own0 = 0, own1 = 0, steps0 = 0, steps1 = 0, evals = 0, bulb_iters = 0;
   int cur_pos = 0, cur_end = 0;
-  SdfEval ev;
-  ev.w = ev.c = mk3(0, 0, 0);
-  ev.dr = ev.m = 0.0f;
-  ev.it = 0;
   while (true) {
     __syncwarp();
-    unsigned idle = __ballot_sync(0xffffffffu, !have);
-    while (idle && !(exhausted && cur_pos >= cur_end)) {
+    unsigned idle0 = __ballot_sync(0xffffffffu, !have0), idle1 = __ballot_sync(0xffffffffu, !have1);
+    while ((idle0 | idle1) && !(exhausted && cur_pos >= cur_end)) {
       if (cur_pos >= cur_end) {
         int b = 0;
-        if (lane == 0) b = atomicAdd(work_ctr, 64);
+        if (lane == 0) b = atomicAdd(work_ctr, SHD_BATCH);
         b = __shfl_sync(0xffffffffu, b, 0);
         if (b >= n_seg) {
           exhausted = true;
           break;
         }
         cur_pos = b;
-        cur_end = min(b + 64, n_seg);
+        cur_end = min(b + SHD_BATCH, n_seg);
       }
       const int avail = cur_end - cur_pos;
-      const int rank = __popc(idle & lt);
-      if (!have && rank < avail) {
-        const int idx = cur_pos + rank;
-        const float4 a = pb.seg_a[idx], b4 = pb.seg_b[idx];
-        st = mk3(a.x, a.y, a.z);
-        max_dist = a.w;
-        dir = mk3(b4.x, b4.y, b4.z);
-        const int ow = __float_as_int(b4.w);
-        bit = ow & 0xff;
-        hk = ow >> 8;
-        owner = pb.seg_owner[idx];
-        first = true;
-        have = true;
-        if (FLAT) eval_start(ev, s_hit[hk], st);
+      const int n0 = __popc(idle0);
+      const int rank0 = __popc(idle0 & lt), rank1 = n0 + __popc(idle1 & lt);
+      if (!have0 && rank0 < avail) {
+        const float4 a = seg_a[cur_pos + rank0], b4 = seg_b[cur_pos + rank0];
+        sx.x = a.x, sy.x = a.y, sz.x = a.z, max_dist.x = a.w, dx.x = b4.x, dy.x = b4.y, dz.x = b4.z;
+        own0 = __float_as_int(b4.w);
+        first0 = have0 = true;
       }
-      cur_pos += min(avail, __popc(idle));
-      idle = __ballot_sync(0xffffffffu, !have);
+      if (!have1 && rank1 < avail) {
+        const float4 a = seg_a[cur_pos + rank1], b4 = seg_b[cur_pos + rank1];
+        sx.y = a.x, sy.y = a.y, sz.y = a.z, max_dist.y = a.w, dx.y = b4.x, dy.y = b4.y, dz.y = b4.z;
+        own1 = __float_as_int(b4.w);
+        first1 = have1 = true;
+      }
+      cur_pos += min(avail, n0 + __popc(idle1));
+      idle0 = __ballot_sync(0xffffffffu, !have0), idle1 = __ballot_sync(0xffffffffu, !have1);
     }
-    if (!__any_sync(0xffffffffu, have)) break;
-    if (have) {
-      float dd = 0.0f;
-      bool ready = true;
-      if (FLAT) {
-        if (eval_more(ev, s_hit[hk])) eval_step(ev, s_hit[hk]);
-        ready = !eval_more(ev, s_hit[hk]);
-        if (ready) dd = eval_finish(ev, s_hit[hk]);
+    if (!__any_sync(0xffffffffu, have0 || have1)) break;
+    float2 px = muladd2(dx, t, sx, k.one), py = muladd2(dy, t, sy, k.one), pz = muladd2(dz, t, sz, k.one);  // dir.mul_add(t, start), sdf.rs:45
+    if (first0) px.x = sx.x, py.x = sy.x, pz.x = sz.x;                                 // dist(start), sdf.rs:30
+    if (first1) px.y = sx.y, py.y = sy.y, pz.y = sz.y;
+    if (!have0) px.x = 100.0f, py.x = 0.0f, pz.x = 0.0f;
+    if (!have1) px.y = 100.0f, py.y = 0.0f, pz.y = 0.0f;
+    const float2 dd = sdf_dist2<V>(k, px, py, pz, bulb_iters);
+    if (have0) {
+      ++evals;
+      bool done;
+      if (first0) {
+        t.x = dd.x, first0 = false, steps0 = 0;
+        done = (t.x != t.x) || (t.x > max_dist.x);
+      } else if (dm::abs(dd.x) < dm::max(oc0, oc1 * t.x)) {
+        atomicAnd(pb.vis + ((unsigned)own0 >> 4), ~(1u << (own0 & 15)));  // occluded
+        done = true;
       } else {
-        dd = sdf_dist(s_hit[hk], first ? st : fma3s(dir, t, st));
+        t.x = t.x + dd.x;
+        ++steps0;
+        done = (t.x != t.x) || steps0 >= max_vis || (t.x > max_dist.x);
       }
-      if (ready) {
-        ++evals;
-        bool done = false;
-        if (first) {
-          t = dd;
-          first = false;
-          steps = 0;
-          done = (t != t) || (t > max_dist);
-        } else if (dm::abs(dd) < dm::max(oc0, oc1 * t)) {
-          atomicAnd(pb.vis + owner, ~(1u << bit));  // occluded
-          done = true;
-        } else {
-          t = t + dd;
-          ++steps;
-          done = (t != t) || steps >= max_vis || (t > max_dist);
-        }
-        if (done)
-          have = false;
-        else if (FLAT)
-          eval_start(ev, s_hit[hk], fma3s(dir, t, st));
+      if (done) have0 = false;
+    }
+    if (have1) {
+      ++evals;
+      bool done;
+      if (first1) {
+        t.y = dd.y, first1 = false, steps1 = 0;
+        done = (t.y != t.y) || (t.y > max_dist.y);
+      } else if (dm::abs(dd.y) < dm::max(oc0, oc1 * t.y)) {
+        atomicAnd(pb.vis + ((unsigned)own1 >> 4), ~(1u << (own1 & 15)));
+        done = true;
+      } else {
+        t.y = t.y + dd.y;
+        ++steps1;
+        done = (t.y != t.y) || steps1 >= max_vis || (t.y > max_dist.y);
       }
+      if (done) have1 = false;
     }
   }
   warp_add(pb.counters + CNT_EVALS_SHADOW, evals);
+  if (V == SDFV_BULB) warp_add(pb.counters + CNT_BULB_ITERS_SHADOW, bulb_iters);
 }
 
 __global__ void __launch_bounds__(128, 8) k_shade_post(const __grid_constant__ DevScene sc, const DevFrame fr, const PassBufs pb,
@@ -1299,7 +808,7 @@ __global__ void __launch_bounds__(128, 8) k_shade_post(const __grid_constant__ D
     const float roulette_sample = samp1(fr, cx.sample, cx.scramble, cx.set1 + 4);
     if (depth >= fr.max_bounces || roulette_sample < roulette_factor) {
       pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
-      pb.term[g] = (TERM_COLOR << 30) | ((unsigned)depth << 20) | (unsigned)s;
+      pb.term[g] = (TERM_COLOR << 30) | ((unsigned)depth << TERM_DEPTH_SHIFT) | (unsigned)s;
       qs[s] = -1;
     } else {
       const f3 no = sp.point + sp.normal * dm::signum(dot(sp.normal, se.wi)) * sp.offset_by;
@@ -1311,7 +820,7 @@ __global__ void __launch_bounds__(128, 8) k_shade_post(const __grid_constant__ D
     }
   } else {  // :189-203
     pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
-    pb.term[g] = ((depth == 0 ? TERM_BACKGROUND : TERM_COLOR) << 30) | ((unsigned)depth << 20) | (unsigned)s;
+    pb.term[g] = ((depth == 0 ? TERM_BACKGROUND : TERM_COLOR) << 30) | ((unsigned)depth << TERM_DEPTH_SHIFT) | (unsigned)s;
     qs[s] = -1;
   }
 }
@@ -1350,160 +859,126 @@ __global__ void __launch_bounds__(CMP_T) k_compact(const PassBufs pb) {
 
 // ------------------------------------------------------------------------------------------
 // K7 film resolve: Tile::add_sample (film.rs:167-172, :54-61) + copy_from_tile (:82-98).
-// The reference adds a pixel's samples in wavefront order: by depth, then by shading-slot
-// order inside the tile.  Each path recorded (depth, slot) when it terminated, so one CTA per
-// pixel sorts its spp paths by that key (bitonic, shared memory) and sums them sequentially
-// in exactly that order -> bit-identical film, no float atomics, deterministic across runs
-// and GPU counts.  Then / spp.
+// The reference adds a pixel's samples in wavefront order: by depth, then by shading-slot order inside
+// the tile.  Each path recorded (depth, slot) when it terminated and its depth-0 slot, so ONE WARP per
+// pixel orders the pixel's spp paths by those keys (in shared memory: 12 B per path; skipped when they
+// already are in order) and 9 lanes run the 9 channel sums strictly sequentially in that order, gathering
+// the payload from L2 -> bit-identical film, no float atomics, deterministic across runs, pass sizes and
+// GPU counts.  Then / spp.  (Round 1 used one 128-thread CTA per pixel with <= 6 busy threads: 8-11 % of
+// HBM; one warp per pixel puts 4-16x more pixels in flight per SM.)
 // ------------------------------------------------------------------------------------------
-#define RES_T 128
-RT_D void bitonic_sort(uint32_t* key, int* val, int np) {
+#define RES_MAX_WARPS 8
+__host__ __device__ inline size_t resolve_smem_per_warp(int np) { return (size_t)np * (2 * sizeof(uint32_t) + 2 * sizeof(uint16_t)); }
+static inline int resolve_warps_per_cta(int np) {
+  int w = (int)((size_t)200 * 1024 / resolve_smem_per_warp(np));
+  return w < 1 ? 0 : (w > RES_MAX_WARPS ? RES_MAX_WARPS : w);
+}
+// in-warp bitonic sort of (key, val) ascending; np a power of two
+RT_D void warp_bitonic(uint32_t* key, uint16_t* val, int np, int lane) {
   for (int k = 2; k <= np; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < np; i += RES_T) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
-          const bool up = (i & k) == 0;
-          const uint32_t a = key[i], b = key[ixj];
-          if ((a > b) == up) {
-            key[i] = b;
-            key[ixj] = a;
-            const int t = val[i];
-            val[i] = val[ixj];
-            val[ixj] = t;
-          }
+      for (int p = lane; p < (np >> 1); p += 32) {
+        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), ixj = i | j;
+        const bool up = (i & k) == 0;
+        const uint32_t a = key[i], b = key[ixj];
+        if ((a > b) == up) {
+          key[i] = b, key[ixj] = a;
+          const uint16_t t = val[i];
+          val[i] = val[ixj], val[ixj] = t;
         }
       }
-      __syncthreads();
+      __syncwarp();
     }
   }
 }
-// sorts (key,val) ascending unless the keys already are (the common case: every path of the
-// pixel hit the same object at depth 0, so slot order == sample order)
-RT_D void sort_if_needed(uint32_t* key, int* val, int np) {
-  int bad = 0;
-  for (int i = threadIdx.x; i + 1 < np; i += RES_T) bad |= key[i] > key[i + 1];
-  if (__syncthreads_or(bad)) bitonic_sort(key, val, np);
-}
-
-static inline size_t resolve_smem_bytes(int np) { return (size_t)np * (2 * 4 + 6 * 4 + 2 * 4 + 3 * 4); }
-
-__global__ void __launch_bounds__(RES_T) k_resolve(const DevFrame fr, const PassBufs pb, float* __restrict__ color,
-                                                   float* __restrict__ alpha, float* __restrict__ background,
-                                                   float* __restrict__ normal, const int np) {
+__global__ void __launch_bounds__(RES_MAX_WARPS * 32) k_resolve(const DevFrame fr, const PassBufs pb, float* __restrict__ color,
+                                                                 float* __restrict__ alpha, float* __restrict__ background,
+                                                                 float* __restrict__ normal, const int np, const int wpc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* key = reinterpret_cast<uint32_t*>(smem_raw);
-  int* val = reinterpret_cast<int*>(key + np);
-  float* rx = reinterpret_cast<float*>(val + np);
-  float *ry = rx + np, *rz = ry + np, *nx = rz + np, *ny = nx + np, *nz = ny + np;
-  uint32_t* s0 = reinterpret_cast<uint32_t*>(nz + np);   // depth-0 slot + 1 (0 = no Alpha/WorldNormal sample)
-  uint32_t* tw = s0 + np;                                // termination word
-  const int ts = blockIdx.y, pl = blockIdx.x, tid = threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  unsigned char* mine = smem_raw + (size_t)warp * resolve_smem_per_warp(np);
+  uint32_t* keyA = reinterpret_cast<uint32_t*>(mine);  // depth-0 slot + 1 of receives_light hits: WorldNormal / Alpha order (integrator.rs:161-169)
+  uint32_t* keyB = keyA + np;                          // (depth, slot) at termination: Color / Background order (integrator.rs:178-203)
+  uint16_t* valA = reinterpret_cast<uint16_t*>(keyB + np);
+  uint16_t* valB = valA + np;
+  const int ts = blockIdx.y, pl = blockIdx.x * wpc + warp;
   const TileGeom tg = tile_geom(fr, pb.tile_ids[ts]);
-  if (pl >= tg.tw * tg.th) return;
+  if (pl >= tg.tw * tg.th) return;  // warp-uniform
   const int xl = pl / tg.th, yl = pl - xl * tg.th;
   const size_t pix = (size_t)(tg.x0 + xl) + (size_t)(tg.y0 + yl) * fr.W;
   const size_t g0 = (size_t)ts * pb.R + (size_t)pl * fr.spp;
+  const float4* __restrict__ nrm0 = pb.nrm0 + g0;
+  const float4* __restrict__ rad = pb.rad + g0;
+  const uint32_t* __restrict__ term = pb.term + g0;
   const float div = (float)fr.spp;
-  // stage the pixel's spp paths in shared memory with coalesced loads
-  for (int i = tid; i < np; i += RES_T) {
-    uint32_t k = 0xffffffffu, slot0 = 0, term = 0;
-    float4 r4 = make_float4(0, 0, 0, 0), n4 = r4;
+  int nA = 0, nB = 0, badA = 0, badB = 0;
+  uint32_t prevA = 0, prevB = 0;  // last key of the previous 32-chunk (lane 31), for the sortedness test
+  for (int base = 0; base < np; base += 32) {
+    const int i = base + lane;
+    uint32_t ka = 0xffffffffu, kb = 0xffffffffu;
     if (i < fr.spp) {
-      r4 = pb.rad[g0 + i];
-      n4 = pb.nrm0[g0 + i];
-      term = pb.term[g0 + i];
-      slot0 = __float_as_uint(n4.w);
-      if (slot0) k = slot0;
+      const uint32_t s0 = __float_as_uint(nrm0[i].w), t = term[i];
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(rad + i));
+      if (s0) ka = s0;
+      if (t >> 30) kb = t & 0x3fffffffu;
     }
-    rx[i] = r4.x, ry[i] = r4.y, rz[i] = r4.z;
-    nx[i] = n4.x, ny[i] = n4.y, nz[i] = n4.z;
-    s0[i] = slot0;
-    tw[i] = term;
-    key[i] = k;
-    val[i] = i;
+    keyA[i] = ka, keyB[i] = kb;
+    valA[i] = valB[i] = (uint16_t)i;
+    nA += __popc(__ballot_sync(0xffffffffu, ka != 0xffffffffu));
+    nB += __popc(__ballot_sync(0xffffffffu, kb != 0xffffffffu));
+    uint32_t pa = __shfl_up_sync(0xffffffffu, ka, 1), pbk = __shfl_up_sync(0xffffffffu, kb, 1);
+    if (lane == 0) pa = prevA, pbk = prevB;
+    badA |= (base + lane > 0) && pa > ka;
+    badB |= (base + lane > 0) && pbk > kb;
+    prevA = __shfl_sync(0xffffffffu, ka, 31), prevB = __shfl_sync(0xffffffffu, kb, 31);
   }
-  __syncthreads();
-  // ---- order A: depth-0 receives_light hits by slot -> WorldNormal, Alpha (integrator.rs:161-169)
-  sort_if_needed(key, val, np);
-  float* g0s = reinterpret_cast<float*>(tw + np);  // 3 x np scratch: channel values gathered in summation order
-  float *g1s = g0s + np, *g2s = g1s + np;
-  for (int i = tid; i < np; i += RES_T) {
-    const bool on = key[i] != 0xffffffffu;
-    const int v = val[i];
-    g0s[i] = on ? nx[v] : 0.0f;
-    g1s[i] = on ? ny[v] : 0.0f;
-    g2s[i] = on ? nz[v] : 0.0f;
-    val[i] = on ? 1 : 0;  // Alpha(1.0) per sample
-  }
-  __syncthreads();
-  if (tid < 4) {  // strictly sequential float sums, in the reference's order; + 0.0f entries are exact no-ops
-    const float* src = tid == 0 ? g0s : tid == 1 ? g1s : g2s;
-    float acc = 0.0f;
-    if (tid < 3) {
-#pragma unroll 8
-      for (int i = 0; i < np; ++i) acc += src[i];
-      normal[3 * pix + tid] = acc / div;
-    } else {
-#pragma unroll 8
-      for (int i = 0; i < np; ++i) acc += (float)val[i];
-      alpha[pix] = acc / div;
-    }
-  }
-  __syncthreads();
-  // ---- order B: terminated paths by (depth, slot) -> Color / Background (integrator.rs:178-203)
-  for (int i = tid; i < np; i += RES_T) {
-    const uint32_t t = tw[i];
-    key[i] = (i < fr.spp && (t >> 30)) ? (t & 0x3fffffffu) : 0xffffffffu;
-    val[i] = i;
-  }
-  __syncthreads();
-  sort_if_needed(key, val, np);
-  // colour in g0s..g2s, background in nx..nz (no longer needed), both in summation order
-  float b0, b1, b2, c0, c1, c2;
-  for (int base = 0; base < np; base += RES_T) {
-    const int i = base + tid;
-    b0 = b1 = b2 = c0 = c1 = c2 = 0.0f;
-    if (i < np && key[i] != 0xffffffffu) {
-      const int v = val[i];
-      const uint32_t kind = tw[v] >> 30;
-      if (kind == TERM_COLOR) c0 = rx[v], c1 = ry[v], c2 = rz[v];
-      if (kind == TERM_BACKGROUND) b0 = rx[v], b1 = ry[v], b2 = rz[v];
-    }
-    __syncthreads();  // all reads of this chunk done before nx..nz / g*s of the same indices are overwritten
-    if (i < np) {
-      g0s[i] = c0, g1s[i] = c1, g2s[i] = c2;
-      nx[i] = b0, ny[i] = b1, nz[i] = b2;
-    }
-  }
-  __syncthreads();
-  if (tid < 6) {
-    const int ch = tid % 3;
-    const float* src = tid < 3 ? (ch == 0 ? g0s : ch == 1 ? g1s : g2s) : (ch == 0 ? nx : ch == 1 ? ny : nz);
+  __syncwarp();
+  if (__any_sync(0xffffffffu, badA)) warp_bitonic(keyA, valA, np, lane);
+  if (__any_sync(0xffffffffu, badB)) warp_bitonic(keyB, valB, np, lane);
+  __syncwarp();
+  // strictly sequential float sums in the reference's order.  lanes 0-2: WorldNormal xyz; 3-5: Color rgb; 6-8: Background rgb.
+  // (A Color lane adds +0.0f for a Background entry and vice versa: exact no-ops, the accumulator can never be -0.)
+  if (lane < 3) {
     float acc = 0.0f;
 #pragma unroll 8
-    for (int i = 0; i < np; ++i) acc += src[i];
-    if (tid < 3)
-      color[3 * pix + ch] = acc / div;
-    else
-      background[3 * pix + ch] = acc / div;
+    for (int i = 0; i < nA; ++i) acc += reinterpret_cast<const float*>(nrm0 + valA[i])[lane];
+    if (normal) normal[3 * pix + lane] = acc / div;
+  } else if (lane < 9) {
+    const int ch = (lane - 3) % 3;
+    const uint32_t want = lane < 6 ? TERM_COLOR : TERM_BACKGROUND;
+    float acc = 0.0f;
+#pragma unroll 8
+    for (int i = 0; i < nB; ++i) {
+      const int v = valB[i];
+      const float x = reinterpret_cast<const float*>(rad + v)[ch];
+      acc += (term[v] >> 30) == want ? x : 0.0f;
+    }
+    float* dst = lane < 6 ? color : background;
+    if (dst) dst[3 * pix + ch] = acc / div;
+  } else if (lane == 9) {
+    if (alpha) alpha[pix] = (float)nA / div;  // Alpha(1.0) per depth-0 receives_light sample: a sum of nA ones is nA exactly
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// multi-GPU film gather helpers: pack this rank's tiles into a dense slab / unpack a slab.
-// slab layout [k][10][tile_w*tile_h], k = rank-local tile ordinal, pixel order x + y*tile_w.
+// multi-GPU film gather helpers.  Slab layout [k][10][tile_w*tile_h], k = rank-local tile ordinal, pixel order
+// x + y*tile_w, channel order color rgb, alpha, background rgb, normal xyz.  `tile_table` holds, for every rank r,
+// `per_rank` entries (its ascending tile indices, padded with -1); slab of rank r starts at r * per_rank * 10 * tp.
+// pack: this rank's tiles -> its slab (grid.x = per_rank, rank = first_rank).  unpack: ONE launch over all ranks'
+// slabs (grid.x = world * per_rank), skipping `skip_rank` (the local one, already in the planes).
+// Tiles are disjoint (film.rs:82-98): the gather moves bytes, it never reduces.
 // ------------------------------------------------------------------------------------------
-__global__ void k_film_pack(int W, int H, int tile_w, int tile_h, int nty, const int* __restrict__ tile_list,
-                            const float* __restrict__ color, const float* __restrict__ alpha,
-                            const float* __restrict__ background, const float* __restrict__ normal, float* __restrict__ slab,
-                            int unpack, float* wcolor, float* walpha, float* wbackground, float* wnormal) {
-  const int k = blockIdx.x;
-  const int tile_id = tile_list[k];
+__global__ void __launch_bounds__(256) k_film_slab(int W, int H, int tile_w, int tile_h, int nty, const int* __restrict__ tile_table, int per_rank,
+                                                   int first_rank, int skip_rank, int unpack, float* __restrict__ slabs, float* color, float* alpha,
+                                                   float* background, float* normal) {
+  const int b = blockIdx.x + first_rank * per_rank;
+  if (b / per_rank == skip_rank) return;
+  const int tile_id = tile_table[b];
+  if (tile_id < 0) return;
   const int tx = tile_id / nty, ty = tile_id % nty;
   const int x0 = tx * tile_w, y0 = ty * tile_h;
   const int tp = tile_w * tile_h;
-  float* sl = slab + (size_t)k * 10 * tp;
+  float* sl = slabs + (size_t)b * 10 * tp;
   for (int p = threadIdx.x; p < tp; p += blockDim.x) {
     const int xl = p % tile_w, yl = p / tile_w;
     const int x = x0 + xl, y = y0 + yl;
@@ -1514,16 +989,31 @@ __global__ void k_film_pack(int W, int H, int tile_w, int tile_h, int nty, const
     }
     const size_t pix = (size_t)x + (size_t)y * W;
     if (!unpack) {
-      for (int c = 0; c < 3; ++c) sl[c * tp + p] = color[3 * pix + c];
-      sl[3 * tp + p] = alpha[pix];
-      for (int c = 0; c < 3; ++c) sl[(4 + c) * tp + p] = background[3 * pix + c];
-      for (int c = 0; c < 3; ++c) sl[(7 + c) * tp + p] = normal[3 * pix + c];
+      for (int c = 0; c < 3; ++c) sl[c * tp + p] = color ? color[3 * pix + c] : 0.0f;
+      sl[3 * tp + p] = alpha ? alpha[pix] : 0.0f;
+      for (int c = 0; c < 3; ++c) sl[(4 + c) * tp + p] = background ? background[3 * pix + c] : 0.0f;
+      for (int c = 0; c < 3; ++c) sl[(7 + c) * tp + p] = normal ? normal[3 * pix + c] : 0.0f;
     } else {
-      for (int c = 0; c < 3; ++c) wcolor[3 * pix + c] = sl[c * tp + p];
-      walpha[pix] = sl[3 * tp + p];
-      for (int c = 0; c < 3; ++c) wbackground[3 * pix + c] = sl[(4 + c) * tp + p];
-      for (int c = 0; c < 3; ++c) wnormal[3 * pix + c] = sl[(7 + c) * tp + p];
+      if (color) for (int c = 0; c < 3; ++c) color[3 * pix + c] = sl[c * tp + p];
+      if (alpha) alpha[pix] = sl[3 * tp + p];
+      if (background) for (int c = 0; c < 3; ++c) background[3 * pix + c] = sl[(4 + c) * tp + p];
+      if (normal) for (int c = 0; c < 3; ++c) normal[3 * pix + c] = sl[(7 + c) * tp + p];
     }
+  }
+}
+// pixels outside the reference's tile grid (film.rs:399-404 drops the last partial tile when 0 < res % tile < tile/2) are
+// never written by a render; device-space planes are cleared there so they do not keep stale caller data (host-space
+// planes start from zeros anyway).
+__global__ void __launch_bounds__(256) k_zero_uncovered(int W, int H, int cov_w, int cov_h, float* color, float* alpha, float* background, float* normal) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)W * H) return;
+  const int x = (int)(i % W), y = (int)(i / W);
+  if (x < cov_w && y < cov_h) return;
+  if (alpha) alpha[i] = 0.0f;
+  for (int c = 0; c < 3; ++c) {
+    if (color) color[3 * i + c] = 0.0f;
+    if (background) background[3 * i + c] = 0.0f;
+    if (normal) normal[3 * i + c] = 0.0f;
   }
 }
 
@@ -1650,6 +1140,31 @@ __global__ void k_kat_sdf_dist(const RaynHitable h, long long n, const float* p3
   if (i >= n) return;
   out[i] = sdf_dist(h, mk3(p3[3 * i], p3[3 * i + 1], p3[3 * i + 2]));
 }
+// packed estimator of the march kernels vs the scalar one: out = sdf_dist2<V>(p[2i], p[2i+1]) per pair; n even
+template <int V>
+__global__ void k_kat_sdf_dist2(const RaynHitable h, const float one, long long n, const float* p3, float* out) {
+  const long long i = 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+  if (i >= n) return;
+  const SdfK k = make_sdfk(h, one);
+  const long long j = i + 1 < n ? i + 1 : i;
+  int it = 0;
+  const float2 d = sdf_dist2<V>(k, f2(p3[3 * i], p3[3 * j]), f2(p3[3 * i + 1], p3[3 * j + 1]), f2(p3[3 * i + 2], p3[3 * j + 2]), it);
+  out[i] = d.x;
+  if (i + 1 < n) out[i + 1] = d.y;
+}
+// Newton division of rt_sdf2.cuh vs IEEE division: counts mismatches of num / x over the n consecutive floats starting at bit pattern first_bits
+__global__ void k_kat_fastdiv(float num, unsigned first_bits, long long n, unsigned long long* mismatches) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int bad = 0;
+  if (i < n) {
+    const float x = __uint_as_float(first_bits + (unsigned)i);
+    const float2 q = fastdiv2(num, f2(x, x));
+    const float ref = num / x;
+    bad = (__float_as_uint(q.x) != __float_as_uint(ref)) + (__float_as_uint(q.y) != __float_as_uint(ref)) +
+          (__float_as_uint(fastdiv1(num, x)) != __float_as_uint(ref));
+  }
+  warp_add(mismatches, bad);
+}
 __global__ void k_kat_sdf_hit(const RaynHitable h, const RaynRenderConsts rc, long long n, const float* o3, const float* d3,
                               const float* t_max, Thr thr, float* out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1713,3 +1228,4 @@ __global__ void k_kat_bsdf(const RaynMaterial m, long long n, const float* n3, c
 }
 
 }  // namespace rt
+

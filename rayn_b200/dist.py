@@ -8,7 +8,9 @@ collective at the end of the frame: an all-gather of dense per-rank tile slabs. 
 disjoint, so the gather moves bytes and never reduces -> the N-GPU film is bit-identical to
 the 1-GPU film.
 
-`torch.distributed` is plumbing only (process group, all_gather on device buffers).
+The GPU path lives behind the C ABI (`rayn_b200_comm_*`, `rayn_b200_render_frame_sharded`, `rayn_b200_film_gather`): the
+context owns the NCCL communicator.  The numpy functions below are the host-logic specification of the same gather
+(used by the gloo CPU tests); `torch.distributed` is plumbing only (it ships the 128-byte communicator id).
 """
 import ctypes as C
 
@@ -88,14 +90,43 @@ def gather_film_arrays(planes, width, height, tile_size, rank, world, all_gather
     return planes
 
 
-class DistFilm:
-    """Device-resident film of one rank + the NCCL gather.  torch is imported lazily."""
+def c_shard_tiles(width, height, tile_size, rank, world):
+    """The shard the C ABI uses (rayn_b200_shard_tiles): must equal shard_tiles(..., "diagonal")."""
+    lib = L.lib()
+    n = lib.rayn_b200_shard_tiles(width, height, tile_size[0], tile_size[1], rank, world, None, 0)
+    if n < 0:
+        raise ValueError("rayn_b200_shard_tiles: bad arguments")
+    arr = (C.c_int32 * max(n, 1))()
+    lib.rayn_b200_shard_tiles(width, height, tile_size[0], tile_size[1], rank, world, arr, n)
+    return list(arr[:n])
 
-    def __init__(self, renderer, width, height, tile_size, rank=0, world=1, group=None, mode="diagonal"):
+
+def init_comm(renderer, rank, world, group=None):
+    """Create the context-owned NCCL communicator (rayn_b200_comm_init_rank).  The 128-byte unique id travels from rank 0
+    to the others through torch.distributed — plumbing only; any transport works (the C++ host could use a file or MPI)."""
+    import torch
+    import torch.distributed as dist
+    lib = L.lib()
+    buf = (C.c_uint8 * L.COMM_ID_BYTES)()
+    if rank == 0:
+        L.check(lib.rayn_b200_comm_unique_id(buf))
+    t = torch.tensor(list(buf), dtype=torch.uint8, device=torch.device("cuda", renderer.device))
+    dist.broadcast(t, src=0, group=group)
+    ident = (C.c_uint8 * L.COMM_ID_BYTES)(*t.cpu().tolist())
+    L.check(lib.rayn_b200_comm_init_rank(renderer.ctx, ident, rank, world), renderer.ctx)
+
+
+class DistFilm:
+    """Device-resident film of one rank.  Multi-GPU goes through the C ABI: the context owns the NCCL communicator and
+    `rayn_b200_render_frame_sharded` renders this rank's tiles and all-gathers the film on the render stream
+    (pack -> ncclAllGather -> one unpack kernel, no host synchronisation in between).  torch is imported lazily and is
+    used only for device memory and to ship the communicator id."""
+
+    def __init__(self, renderer, width, height, tile_size, rank=0, world=1, group=None):
         import torch
         self.torch = torch
         self.r, self.w, self.h, self.tile = renderer, width, height, tuple(tile_size)
-        self.rank, self.world, self.group, self.mode = rank, world, group, mode
+        self.rank, self.world = rank, world
         dev = torch.device("cuda", renderer.device)
         npx = width * height
         self.store = torch.zeros(10 * npx, dtype=torch.float32, device=dev)
@@ -103,37 +134,30 @@ class DistFilm:
                          "background": self.store[4 * npx: 7 * npx], "normal": self.store[7 * npx:]}
         self.planes = L.RaynFilmPlanes(self.planes_t["color"].data_ptr(), self.planes_t["alpha"].data_ptr(),
                                        self.planes_t["background"].data_ptr(), self.planes_t["normal"].data_ptr(), L.MEM_DEVICE)
-        ntx, nty = tile_grid(width, height, *self.tile)
-        self.shards = [shard_tiles(ntx, nty, r, world, mode) for r in range(world)]
-        self._shard_arrays = [(C.c_int32 * max(len(t), 1))(*t) for t in self.shards]
-        self.tile_list = self.shards[rank] if world > 1 else None
+        self.tile_list = c_shard_tiles(width, height, self.tile, rank, world) if world > 1 else None
         if world > 1:
-            n = max(len(t) for t in self.shards) * 10 * self.tile[0] * self.tile[1]
-            self.slab = torch.zeros(n, dtype=torch.float32, device=dev)
-            self.all_slabs = torch.zeros(n * world, dtype=torch.float32, device=dev)
+            init_comm(renderer, rank, world, group)
 
     def render(self, frame_desc):
         """Render this rank's tiles into the device film (frame_desc carries this rank's tile list)."""
         self.r.render(frame_desc, self.planes)
 
     def gather(self):
-        """All ranks end with the complete film.  One NCCL all-gather of dense tile slabs."""
+        """All ranks end with the complete film: rayn_b200_film_gather (asynchronous) + sync."""
         if self.world == 1:
             return
-        torch, lib = self.torch, L.lib()
-        import torch.distributed as dist
-        tw, th = self.tile
-        ip = C.POINTER(C.c_int32)
-        L.check(lib.rayn_b200_film_pack_tiles(self.r.ctx, self.w, self.h, tw, th, C.cast(self._shard_arrays[self.rank], ip),
-                                              len(self.shards[self.rank]), C.byref(self.planes), self.slab.data_ptr()), self.r.ctx)
-        dist.all_gather_into_tensor(self.all_slabs, self.slab, group=self.group)
-        torch.cuda.current_stream().synchronize()
-        n = self.slab.numel()
-        for r in range(self.world):
-            if r == self.rank:
-                continue
-            L.check(lib.rayn_b200_film_unpack_tiles(self.r.ctx, self.w, self.h, tw, th, C.cast(self._shard_arrays[r], ip), len(self.shards[r]),
-                                                    self.all_slabs[r * n:(r + 1) * n].data_ptr(), C.byref(self.planes)), self.r.ctx)
+        lib = L.lib()
+        L.check(lib.rayn_b200_film_gather(self.r.ctx, self.w, self.h, self.tile[0], self.tile[1], C.byref(self.planes)), self.r.ctx)
+        L.check(lib.rayn_b200_sync(self.r.ctx), self.r.ctx)
+
+    def render_gathered(self, frame_desc, planes=None):
+        """One call: shard render + gather (rayn_b200_render_frame_sharded); 1 GPU: plain render_frame."""
+        planes = planes if planes is not None else self.planes
+        lib = L.lib()
+        if self.world == 1:
+            L.check(lib.rayn_b200_render_frame(self.r.ctx, C.byref(frame_desc), C.byref(planes)), self.r.ctx)
+        else:
+            L.check(lib.rayn_b200_render_frame_sharded(self.r.ctx, C.byref(frame_desc), C.byref(planes)), self.r.ctx)
 
     def to_host(self):
         return {k: v.cpu().numpy() for k, v in self.planes_t.items()}

@@ -29,7 +29,7 @@ class FrameInputs:
     FilterImportanceSampler table (film.rs:429).  Built by the pure-CPU helpers of the C ABI."""
 
     def __init__(self, width, height, samples, integrator, filt=None, frame=1):
-        lib = L.lib()
+        lib = L.host_lib()  # pure CPU: building frame inputs must not need (or map) the CUDA library
         filt = filt or BlackmanHarrisFilter(1.5)
         self.width, self.height, self.samples, self.spp, self.frame = width, height, samples, 4 * samples, frame
         self.sets_1d = 1 + integrator.requested_1d_sample_sets()  # film.rs:431
@@ -69,7 +69,7 @@ def make_frame_desc(width, height, tile_size, samples, integrator, frame, time_r
 
 def tile_grid(width, height, tile_w, tile_h):
     nx, ny = C.c_int32(), C.c_int32()
-    L.check(L.lib().rayn_b200_host_tile_grid(width, height, tile_w, tile_h, C.byref(nx), C.byref(ny)))
+    L.check(L.host_lib().rayn_b200_host_tile_grid(width, height, tile_w, tile_h, C.byref(nx), C.byref(ny)))
     return nx.value, ny.value
 
 
@@ -150,6 +150,17 @@ class Renderer:
         out = np.empty(len(p), np.float32)
         L.check(self._lib.rayn_b200_kat_sdf_dist(self._ctx, C.byref(hitable), len(p), _fptr(p), _fptr(out)), self._ctx)
         return out
+
+    def kat_sdf_dist2(self, hitable, points, variant=-1):
+        p = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        out = np.empty(len(p), np.float32)
+        L.check(self._lib.rayn_b200_kat_sdf_dist2(self._ctx, C.byref(hitable), variant, len(p), _fptr(p), _fptr(out)), self._ctx)
+        return out
+
+    def kat_fastdiv(self, num, first_bits, n):
+        bad = C.c_int64(-1)
+        L.check(self._lib.rayn_b200_kat_fastdiv(self._ctx, num, first_bits, n, C.byref(bad)), self._ctx)
+        return bad.value
 
     def kat_sdf_hit(self, hitable, consts, origins, dirs, t_max, thr_scale, thr_const=0):
         o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)

@@ -28,7 +28,28 @@ def test_every_declared_symbol_is_exported_and_bound():
     assert declared == set(L.SYMBOLS), f"binding/header mismatch: {declared ^ set(L.SYMBOLS)}"
     for name in declared:
         assert hasattr(lib, name), f"librayn_b200.so does not export {name}"
-    assert lib.rayn_b200_abi_version() == 1
+    assert lib.rayn_b200_abi_version() == 2
+    assert lib.rayn_b200_muladd_fused() == (1 if L.MULADD_FUSED else 0)
+
+
+def test_all_library_variants_load_and_export_the_abi():
+    """default (mul_add unfused = stock rayn build), _fma (fused) and the legacy TEST build export the same ABI; the
+    host-inputs library exports the pure-CPU builders without pulling in the CUDA runtime."""
+    _ensure_built()
+    from rayn_b200 import _lib as L
+    bdir = os.path.dirname(L.LIB_PATH)
+    for name, fused in (("librayn_b200.so", 0), ("librayn_b200_fma.so", 1), ("librayn_b200_legacy.so", 0)):
+        l = C.CDLL(os.path.join(bdir, name))
+        for sym in L.SYMBOLS:
+            assert hasattr(l, sym), f"{name} lacks {sym}"
+        assert l.rayn_b200_muladd_fused() == fused
+    h = C.CDLL(L.HOSTLIB_PATH)
+    for sym in L.HOST_SYMBOLS:
+        assert hasattr(h, sym)
+    ldd = subprocess.run(["ldd", L.HOSTLIB_PATH], capture_output=True, text=True).stdout
+    assert "cudart" not in ldd and "libcuda" not in ldd
+    ldd = subprocess.run(["ldd", L.LIB_PATH], capture_output=True, text=True).stdout
+    assert "nccl" not in ldd, "NCCL must be resolved with dlopen at the first comm call, not at load time"
 
 
 def test_struct_layouts_match_the_c_compiler(tmp_path):

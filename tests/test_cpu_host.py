@@ -169,3 +169,16 @@ def test_cpp_host_flattens_the_same_scene_as_the_python_host(tmp_path):
         want = b"".join(bytes(d.hitables[i]) for i in range(d.n_hitables)) + b"".join(bytes(d.materials[i]) for i in range(d.n_materials)) + \
             b"".join(bytes(d.lights[i]) for i in range(d.n_lights)) + bytes(d.camera) + bytes(d.volume)
         assert out.read_bytes() == want, f"config {n}"
+
+
+def test_c_abi_shard_equals_the_python_specification():
+    """rayn_b200_shard_tiles (what render_frame_sharded / the NCCL gather use) is pure host arithmetic: callable without a GPU."""
+    from rayn_b200.dist import c_shard_tiles
+    for w, h, world in ((176, 104, 3), (100, 40, 2), (1920, 1080, 8), (7680, 4320, 8), (16, 16, 4)):
+        ntx, nty = tile_grid(w, h, 16, 16)
+        seen = []
+        for rank in range(world):
+            t = c_shard_tiles(w, h, (16, 16), rank, world)
+            assert t == shard_tiles(ntx, nty, rank, world, "diagonal")
+            seen += t
+        assert sorted(seen) == list(range(ntx * nty))

@@ -14,6 +14,7 @@ from rayn_b200 import configs
 from helpers import CH, assert_bit_equal, random_rays, small_config
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLD_SUFFIX = "_fma" if L.MULADD_FUSED else ""  # fixtures exist for both `wide` mul_add variants (oracle/README.md A6)
 TR = configs.frame_time_range(1)
 
 
@@ -159,7 +160,7 @@ def test_oracle_reproduces_committed_golden(oracle, name):
     n, res, samples, mb = GOLDEN_CASES[name]
     c, inp = small_config(n, res, samples, mb)
     o, _ = oracle.render(c["world"], c["camera"], inp, (16, 16), c["integrator"], TR)
-    g = np.load(os.path.join(GOLD, name + ".npz"))
+    g = np.load(os.path.join(GOLD, name + GOLD_SUFFIX + ".npz"))
     for ch in CH:
         assert_bit_equal(o[ch], g[ch], f"{name} {ch}")
 

@@ -201,14 +201,3 @@ def test_time_varying_sphere_and_camera(renderer, oracle):
     g_frozen, _ = _both(renderer, oracle, world, still_cam, res, 2, 3)
     assert not np.array_equal(g_still_cam["color"], g_frozen["color"])
     assert not np.array_equal(g_move["color"], g_still_cam["color"])
-    # the non-default kernel families refuse motion instead of silently ignoring it
-    hitables.items[2] = Sphere(Linear(Vec3(-3.0, 1.9, 0.0), Vec3(40.0, 0.0, 0.0)), 0.4, grey)
-    r = Renderer(0, flags=L.FLAG_SIMPLE_MARCH)
-    try:
-        r.upload_scene(world, still_cam)
-        integ = PathTracingIntegrator(1, 2)
-        with pytest.raises(L.RaynError) as e:
-            r.render_host(FrameInputs(48, 40, 1, integ), (16, 16), integ, TR)
-        assert e.value.code == L.RAYN_ERR_UNSUPPORTED
-    finally:
-        r.close()

@@ -60,6 +60,45 @@ def test_sdf_dist_bit_equal(renderer, oracle, kind):
     assert_bit_equal(renderer.kat_sdf_dist(h, p), oracle.kat_sdf_dist(h, p), f"{kind} dist")
 
 
+@pytest.mark.parametrize("kind,variants", [("mandelbox", (-1, 0, 1, 2)), ("mandelbulb", (-1, 3))])
+def test_packed_two_point_estimator_bit_equal(renderer, oracle, kind, variants):
+    """rt_sdf2.cuh: the f32x2 (FFMA2/FMUL2/FADD2) two-point estimators the march kernels run, every specialisation,
+    against the oracle's 4-lane SSE estimator; odd point count exercises the half-filled last pair."""
+    desc, keep, h = _sdf(kind)
+    rng = np.random.default_rng(5)
+    p = rng.uniform(-2.5, 2.5, size=(100_001, 3)).astype(np.float32)
+    p[:20_000] *= 0.2          # inside the sphere-fold radius: the division matters there
+    p[20_000:20_100] *= 40.0   # far field
+    p[0] = 0.0
+    p[1] = [0.0, 0.0, 1.0]
+    p[2] = np.nan
+    p[3] = [np.inf, 0.0, 0.0]
+    p[4] = [1e-30, -1e-30, 0.0]
+    ref = oracle.kat_sdf_dist(h, p)
+    for v in variants:
+        assert_bit_equal(renderer.kat_sdf_dist2(h, p, v), ref, f"{kind} packed dist variant {v}")
+    if kind == "mandelbox":  # non-default fold constants and iteration counts through the run-time specialisations
+        import copy
+        for iters, l, mn, fx, sc in [(7, 1.0, 0.25, 1.0, 2.0), (15, 0.8, 1e-4, 3.61, -1.5), (3, 1.5, 0.5, 0.4, -2.1)]:
+            h2 = copy.copy(h)
+            h2.iterations, h2.box_l, h2.min_rad_sq, h2.fixed_rad_sq, h2.scale = iters, l, mn, fx, sc
+            ref2 = oracle.kat_sdf_dist(h2, p)
+            for v in (-1, 0, 2):
+                assert_bit_equal(renderer.kat_sdf_dist2(h2, p, v), ref2, f"mandelbox {iters, l, mn, fx, sc} variant {v}")
+
+
+def test_fastdiv_equals_ieee_division(renderer):
+    """The Newton division of the Mandelbox sphere fold (rt_sdf2.cuh::fastdiv2, no FCHK slow path) against IEEE `/`,
+    EXHAUSTIVELY over every float the clamped divisor can take for the reference's constants (setup.rs:84:
+    min 0.01^2, fixed 1.9^2), and over every divisor in [2^-10, 2^10) for a few other numerators."""
+    mn, fx = np.float32(0.01) * np.float32(0.01), np.float32(1.9) * np.float32(1.9)
+    lo, hi = int(mn.view(np.uint32)), int(fx.view(np.uint32))
+    assert renderer.kat_fastdiv(float(fx), lo, hi - lo + 1) == 0
+    lo, hi = int(np.float32(2.0 ** -10).view(np.uint32)), int(np.float32(2.0 ** 10).view(np.uint32))
+    for num in (1.0, 3.0, 0.7, 1e3, 1.1754944e-3):
+        assert renderer.kat_fastdiv(num, lo, hi - lo) == 0, num
+
+
 @pytest.mark.parametrize("kind", ["mandelbox", "mandelbulb"])
 @pytest.mark.parametrize("thr", [(0.000563, 0), (0.0002, 0), (0.0006, 0), (0.001, 1)])
 def test_sphere_march_bit_equal(renderer, oracle, kind, thr):
@@ -264,32 +303,67 @@ def test_error_codes():
 # ---- GPU vs the committed golden fixtures (tests/golden/*.npz, generated by make_golden.py) ----
 def test_gpu_matches_committed_golden(renderer):
     import os
-    from test_cpu_oracle import GOLD, GOLDEN_CASES
+    from test_cpu_oracle import GOLD, GOLD_SUFFIX, GOLDEN_CASES
     for name, (n, res, samples, mb) in sorted(GOLDEN_CASES.items()):
         c, inp = small_config(n, res, samples, mb)
         renderer.upload_scene(c["world"], c["camera"])
         g = renderer.render_host(inp, (16, 16), c["integrator"], TR)
-        gold = np.load(os.path.join(GOLD, name + ".npz"))
+        gold = np.load(os.path.join(GOLD, name + GOLD_SUFFIX + ".npz"))
         for ch in CH:
             assert_bit_equal(g[ch], gold[ch], f"golden {name} {ch}")
 
 
-def test_alternative_kernel_families_stay_bit_exact(oracle):
-    """RAYN_FLAG_SIMPLE_MARCH = v0 one-thread-per-ray kernels, RAYN_FLAG_BLOCK_POOL = v2 per-block
-    refill / shadow pool; the default is v3 (pass-wide persistent march kernels).  All three
-    families must give the oracle's bits."""
-    for n, res, samples, mb in [(3, (48, 48), 2, 4), (4, (32, 32), 1, 2)]:
+def _run_suite_variant(env_extra, args):
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, **env_extra)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-p", "no:cacheprovider"] + args, cwd=root, env=env,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1500:]
+    return r.stdout
+
+
+@pytest.mark.skipif(L.MULADD_FUSED or L.LEGACY, reason="already inside a variant run")
+def test_fused_mul_add_variant_passes_the_parity_suite():
+    """oracle/README.md A6: `wide` f32x4::mul_add is unfused in a stock `cargo run --release` build of rayn (the default
+    here) and fused with `-C target-feature=+fma`.  Both variants of the kernels (librayn_b200_fma.so) and of the oracle
+    (librayn_oracle_fma.so) exist; this runs the stage, packet-order, image and golden tests again in the fused variant."""
+    out = _run_suite_variant({"RAYN_MULADD_FUSED": "1"}, ["tests/test_gpu_parity.py", "-k", "not full_size and not variant and not legacy and not cpp_host"])
+    assert " passed" in out
+
+
+@pytest.mark.skipif(L.MULADD_FUSED or L.LEGACY, reason="already inside a variant run")
+def test_legacy_one_thread_per_ray_kernels_agree():
+    """TEST build librayn_b200_legacy.so (-DRAYN_LEGACY_KERNELS): the round-1 v0 kernels (one thread per ray, shadow marches
+    fused into shading, scalar arithmetic, no queues) are a structurally independent second implementation; with
+    RAYN_FLAG_SIMPLE_MARCH they must give the oracle's bits too."""
+    out = _run_suite_variant({"RAYN_B200_LEGACY": "1"}, ["tests/test_gpu_parity.py", "-k", "legacy_family_inner or image_bit_exact"])
+    assert " passed" in out
+
+
+@pytest.mark.skipif(not L.LEGACY, reason="needs RAYN_B200_LEGACY=1 (run by test_legacy_one_thread_per_ray_kernels_agree)")
+def test_legacy_family_inner(oracle):
+    for n, res, samples, mb in [(3, (48, 48), 2, 4), (4, (32, 32), 1, 2), (2, (48, 32), 2, 3)]:
         c, inp = small_config(n, res, samples, mb)
         o, _ = oracle.render(c["world"], c["camera"], inp, (16, 16), c["integrator"], TR)
-        for flag in (L.FLAG_SIMPLE_MARCH, L.FLAG_BLOCK_POOL, L.FLAG_FLATTEN):
-            r = Renderer(0, flags=flag)
-            try:
-                r.upload_scene(c["world"], c["camera"])
-                g = r.render_host(inp, (16, 16), c["integrator"], TR)
-            finally:
-                r.close()
-            for ch in CH:
-                assert_bit_equal(g[ch], o[ch], f"kernel family {flag} cfg{n} {ch}")
+        r = Renderer(0, flags=L.FLAG_SIMPLE_MARCH)
+        try:
+            r.upload_scene(c["world"], c["camera"])
+            g = r.render_host(inp, (16, 16), c["integrator"], TR)
+        finally:
+            r.close()
+        for ch in CH:
+            assert_bit_equal(g[ch], o[ch], f"legacy kernels cfg{n} {ch}")
+
+
+def test_simple_march_flag_is_rejected_by_the_product_library():
+    if L.LEGACY:
+        pytest.skip("legacy build")
+    with pytest.raises(L.RaynError) as e:
+        Renderer(0, flags=L.FLAG_SIMPLE_MARCH)
+    assert e.value.code == L.RAYN_ERR_UNSUPPORTED
 
 
 def test_cpp_host_renders_the_same_film_as_the_python_host(renderer, tmp_path):
@@ -348,6 +422,71 @@ def test_full_size_config_tile_sample_matches_oracle(oracle, n, k):
     assert g["alpha"].min() >= 0 and g["alpha"].max() <= 1.0
     covered = (g["alpha"] > 0) | (g["background"].reshape(-1, 3).sum(1) > 0)
     assert covered.mean() > 0.999  # every camera ray ends on the sky sphere or the fractal
+
+
+SAMPLED_TILES = ((0.5, 0.5), (0.4, 0.55), (0.62, 0.45), (0.05, 0.9), (0.33, 0.37), (0.7, 0.62))
+
+
+@pytest.mark.parametrize("n", [4, 5])
+def test_full_size_multi_gpu_configs_sampled_tiles_match_oracle(oracle, n):
+    """BASELINE configs 4 (2048x2048, 256 spp, volume + thin lens) and 5 (7680x4320, 1024 spp, 8 bounces) at their FULL
+    resolution and spp: GPU and oracle both render the same six 16x16 tiles (picked across the fractal and the sky) of the
+    full-size frame through `tile_list`; tiles are independent (film.rs:439-627), so they must agree bit for bit.  Full
+    frames of these sizes are what the multi-GPU bench renders; here one GPU and a few CPU seconds suffice."""
+    c = configs.baseline_config(n)
+    w, h = c["res"]
+    inp = FrameInputs(w, h, c["samples"], c["integrator"])
+    from rayn_b200.film import tile_grid
+    ntx, nty = tile_grid(w, h, 16, 16)
+    tiles = sorted({int(fx * ntx) * nty + int(fy * nty) for fx, fy in SAMPLED_TILES})
+    r = Renderer(0)
+    try:
+        r.upload_scene(c["world"], c["camera"])
+        g = r.render_host(inp, (16, 16), c["integrator"], TR, tile_list=tiles)
+        st = r.stats()
+    finally:
+        r.close()
+    assert st.paths == len(tiles) * 256 * c["spp"]
+    o, info = oracle.render(c["world"], c["camera"], inp, (16, 16), c["integrator"], TR, tile_list=tiles)
+    assert info["tiles"] == len(tiles)
+    assert st.extend_rays == info["extend_rays"] and st.shade_lanes == info["shade_lanes"]
+    for ch in CH:
+        assert_bit_equal(g[ch], o[ch], f"full-size cfg{n} sampled tiles {ch}")
+    lit = g["color"].reshape(-1, 3).sum(1) + g["background"].reshape(-1, 3).sum(1)
+    assert (lit > 0).sum() >= 0.9 * len(tiles) * 256 and g["alpha"].max() > 0  # the sample covers fractal and sky
+
+
+def test_null_planes_are_skipped_like_absent_film_channels(renderer):
+    """Film<N> may hold any subset of channels (film.rs:175-203); add_sample ignores absent ones (:167-172)."""
+    c, inp = small_config(3, (48, 32), 1, 2)
+    renderer.upload_scene(c["world"], c["camera"])
+    full = renderer.render_host(inp, (16, 16), c["integrator"], TR)
+    w, h = 48, 32
+    color = np.zeros(3 * w * h, np.float32)
+    alpha = np.zeros(w * h, np.float32)
+    p = L.RaynFilmPlanes(color.ctypes.data, alpha.ctypes.data, None, None, L.MEM_HOST)
+    from rayn_b200.film import make_frame_desc
+    f = make_frame_desc(w, h, (16, 16), inp.samples, c["integrator"], 1, TR, tuple(a.ctypes.data for a in inp.arrays()), L.MEM_HOST, 0, 1,
+                        (inp.sets_1d, inp.sets_2d))
+    renderer.render(f, p)
+    assert_bit_equal(color, full["color"], "color only")
+    assert_bit_equal(alpha, full["alpha"], "alpha only")
+    with pytest.raises(L.RaynError) as e:
+        renderer.render(f, L.RaynFilmPlanes(None, None, None, None, L.MEM_HOST))
+    assert e.value.code == L.RAYN_ERR_INVALID_ARG
+
+
+def test_statistics_are_consistent(renderer, oracle):
+    """evals / iterations / lanes reported by RaynStats feed bench.py's flop figures: cross-check them."""
+    c, inp = small_config(2, (64, 64), 2, 3)
+    renderer.upload_scene(c["world"], c["camera"])
+    renderer.render_host(inp, (16, 16), c["integrator"], TR)
+    st = renderer.stats()
+    assert st.sdf_evals_extend > 0 and st.sdf_evals_shadow > 0 and st.sdf_evals_normals > 0
+    assert st.sdf_evals_normals % 4 == 0 and st.sdf_evals_normals <= 4 * st.shade_lanes
+    # the authored Mandelbulb leaves its loop between 0 and 8 iterations: the counted iterations must be below the cap
+    assert 0 < st.bulb_iters_extend < 8 * st.sdf_evals_extend
+    assert 0 < st.bulb_iters_shadow < 8 * st.sdf_evals_shadow
 
 
 # ---- K4 stage tests: light sampling and BSDFs, host vs device (SURVEY T0) -------------------------
