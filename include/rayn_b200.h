@@ -222,6 +222,9 @@ typedef struct RaynConfig {
 #define RAYN_FLAG_SIMPLE_MARCH 2 /* TEST BUILD ONLY (-DRAYN_LEGACY_KERNELS, librayn_b200_legacy.so): round-1 v0
                                     one-thread-per-ray kernels; RAYN_ERR_UNSUPPORTED in the product library */
 
+#define RAYN_FLAG_NO_GRAPH 16    /* launch every kernel directly; by default small single-pass frames (launch bound) are
+                                    captured once into a CUDA graph and replayed with one launch                */
+
 #define RAYN_STAT_KERNELS 12
 typedef struct RaynStats {
   int64_t launches;                 /* kernels launched by the last render call            */
@@ -238,7 +241,7 @@ typedef struct RaynStats {
   int64_t sdf_evals_normals;        /* SDF dist() evaluations of get_shading_info (4 per SDF shading lane) */
   int64_t bulb_iters_extend;        /* Mandelbulb iterations actually run inside K2 (data dependent)       */
   int64_t bulb_iters_shadow;        /* ... inside K5                                                       */
-  int64_t reserved_;
+  int64_t reserved_;                /* 1 when the last frame was replayed from the captured CUDA graph     */
 } RaynStats;
 
 /* indices into kernel_ms / kernel_launches */

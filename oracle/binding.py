@@ -30,8 +30,11 @@ def build(force=False):
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            build()
+        try:
+            build()  # mtime check: do not test against an oracle that is older than its sources
+        except Exception:
+            if not os.path.exists(LIB_PATH):
+                raise
         l = C.CDLL(LIB_PATH)
         l.rayn_oracle_selfcheck.restype = C.c_int32
         l.rayn_oracle_render_frame.restype = C.c_int32

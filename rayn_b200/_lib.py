@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 MULADD_FUSED = os.environ.get("RAYN_MULADD_FUSED", "0") == "1"
 LEGACY = os.environ.get("RAYN_B200_LEGACY", "0") == "1"
 LIB_NAME = "librayn_b200_fma.so" if MULADD_FUSED else ("librayn_b200_legacy.so" if LEGACY else "librayn_b200.so")
+LIB_NAME = os.environ.get("RAYN_B200_LIB", LIB_NAME)  # tuning experiments: an explicitly named build
 LIB_PATH = os.path.join(_HERE, "_build", LIB_NAME)
 HOSTLIB_PATH = os.path.join(_HERE, "_build", "librayn_hostinputs.so")
 
@@ -37,7 +38,7 @@ CAMERA_PINHOLE, CAMERA_THINLENS, CAMERA_ORTHOGRAPHIC = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 POST_COLOR_PLUS_BACKGROUND, POST_COLOR_ALPHA, POST_COLOR_ONLY, POST_BACKGROUND, POST_WORLD_NORMAL, POST_ALPHA = range(6)
 POST_BYTES = (3, 4, 3, 3, 3, 1)
-FLAG_TIMING, FLAG_SIMPLE_MARCH = 1, 2
+FLAG_TIMING, FLAG_SIMPLE_MARCH, FLAG_NO_GRAPH = 1, 2, 16
 STAT_KERNELS = 12
 KERNEL_NAMES = ["raygen", "extend", "bin", "shade_pre", "shadow", "shade_post", "compact", "resolve", "misc", "normals", "extend_spheres", "gather"]
 

@@ -32,6 +32,9 @@ VARIANTS = {  # file name -> extra defines
     "librayn_b200_fma.so": ["-DRAYN_MULADD_FUSED=1"],
     "librayn_b200_legacy.so": ["-DRAYN_MULADD_FUSED=0", "-DRAYN_LEGACY_KERNELS"],
 }
+if os.environ.get("RAYN_BUILD_EXPERIMENTS"):  # tuning experiments only (selected with RAYN_B200_LIB=<file name>)
+    for occ in os.environ["RAYN_BUILD_EXPERIMENTS"].split(","):
+        VARIANTS[f"librayn_b200_occ{occ}.so"] = ["-DRAYN_MULADD_FUSED=0", f"-DRAYN_MARCH_OCC={occ}"]
 HOSTINPUTS = os.path.join(OUT_DIR, "librayn_hostinputs.so")
 
 

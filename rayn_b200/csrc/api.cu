@@ -95,7 +95,17 @@ struct RaynContext {
   int job_w = 0, job_h = 0, job_tw = 0, job_th = 0, job_spp = 0, job_nty = 0;
   unsigned long long h_counters[CNT_TOTAL];
   RaynComm comm;
+  // CUDA graph of the last small single-pass frame (launch-bound frames: the whole per-depth kernel sequence replays as one launch)
+  cudaGraphExec_t graph_exec = nullptr;
+  uint64_t graph_key = 0;
+  RaynStats graph_stats;  // launch counts recorded while capturing
 };
+
+static uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
+  const unsigned char* p = (const unsigned char*)data;
+  for (size_t i = 0; i < n; ++i) h = (h ^ p[i]) * 1099511628211ull;
+  return h;
+}
 
 static int32_t fail(RaynContext* ctx, int32_t code, const char* fmt, ...) {
   char buf[512];
@@ -246,6 +256,9 @@ struct DevTmp {
     if (*e != cudaSuccess) return nullptr;
     ptrs.push_back(d);
     if (h) *e = cudaMemcpy(d, h, n * sizeof(T), cudaMemcpyHostToDevice);
+    // cudaMemcpy from PAGEABLE memory returns once the data is staged; the DMA may still be in flight, and the test kernels
+    // run on a non-blocking stream that does not order against the legacy stream: wait for the copy to land.
+    if (h && *e == cudaSuccess) *e = cudaDeviceSynchronize();
     return d;
   }
 };
@@ -359,6 +372,7 @@ void rayn_b200_destroy(RaynContext* ctx) {
   cudaFree(ctx->d_post);
   cudaFree(ctx->d_s1), cudaFree(ctx->d_s2), cudaFree(ctx->d_scr), cudaFree(ctx->d_fis), cudaFree(ctx->d_planes);
   for (auto& t : ctx->timed) cudaEventDestroy(t.a), cudaEventDestroy(t.b);
+  if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
   cudaEventDestroy(ctx->ev0), cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -464,6 +478,15 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
   if (wpc < 1 || np > 65536) return fail(ctx, RAYN_ERR_UNSUPPORTED, "spp = %d: the film resolve holds 12 B per sample of a pixel in shared memory (max 16384 spp)", spp);
   const int R = (int)R64, QS = R + 4 * n_hit;
   CU(cudaSetDevice(ctx->device));
+  {  // a previous call that failed half way through a graph capture must not leave the stream capturing
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(ctx->stream, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) {
+      cudaGraph_t g = nullptr;
+      cudaStreamEndCapture(ctx->stream, &g);
+      if (g) cudaGraphDestroy(g);
+    }
+    cudaGetLastError();
+  }
 
   DevFrame fr;
   fr.W = f->width, fr.H = f->height, fr.tile_w = f->tile_w, fr.tile_h = f->tile_h;
@@ -536,6 +559,13 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
     motion |= ctx->scene.hit[i].kind == RAYN_HITABLE_SPHERE && (ctx->scene.hit[i].center_velocity[0] != 0.0f || ctx->scene.hit[i].center_velocity[1] != 0.0f ||
                                                                  ctx->scene.hit[i].center_velocity[2] != 0.0f);
   if (motion && simple) return fail(ctx, RAYN_ERR_UNSUPPORTED, "time-varying sphere centres are not supported by the legacy test kernels");
+  // leading analytic spheres run inside raygen / shade_post (rt_kernels.cuh::fold_head); -1 = not folded (moving spheres need
+  // the extend packet's lane-0 time; the legacy test kernels do the whole fold themselves)
+  int fold_pre = -1;
+  if (!motion && !simple) {
+    fold_pre = 0;
+    while (fold_pre < n_hit && ctx->scene.hit[fold_pre].kind == RAYN_HITABLE_SPHERE) ++fold_pre;
+  }
   const bool volume_on = ctx->scene.vol.has_scattering != 0 && ctx->scene.n_lights > 0;
   const int ns = volume_on ? 4 * (1 + vm) : 4;               // light samples per path per depth
   const int seg_per_path = simple ? 0 : ns * n_sdf;          // worst case shadow segments per path per depth, all SDF queues
@@ -564,15 +594,45 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
   const size_t res_smem = resolve_smem_per_warp(np) * wpc;
   CU(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem));
 
+  // Small single-pass frames are launch bound (config 1: ~20 launches of a few microseconds each): capture the whole kernel
+  // sequence of the pass once and replay it as ONE graph launch while nothing that is baked into the launches changes
+  // (scene, frame geometry, every pointer, the tile set).
+  const bool single_pass = my_tiles.size() <= (size_t)tiles_per_pass;
+  const bool use_graph = single_pass && !my_tiles.empty() && !(ctx->flags & (RAYN_FLAG_TIMING | RAYN_FLAG_NO_GRAPH)) && !ctx->qlog_enabled &&
+                         (int64_t)my_tiles.size() * R <= ((int64_t)8 << 20);
+  bool capturing = false, replayed = false;
+  uint64_t key = 0;
+  if (use_graph) {
+    PassBufs kpb = pb;
+    kpb.n_tiles = (int)my_tiles.size();
+    key = fnv1a(1469598103934665603ull, &ctx->scene, sizeof ctx->scene);
+    key = fnv1a(key, &fr, sizeof fr);
+    key = fnv1a(key, &kpb, sizeof kpb);
+    float* planes4[4] = {p_color, p_alpha, p_bg, p_normal};
+    key = fnv1a(key, planes4, sizeof planes4);
+    const int misc[6] = {np, wpc, mb, fold_pre, simple ? 1 : 0, motion ? 1 : 0};
+    key = fnv1a(key, misc, sizeof misc);
+    key = fnv1a(key, my_tiles.data(), my_tiles.size() * sizeof(int));
+    if (ctx->graph_exec && ctx->graph_key == key) {
+      CU(cudaMemcpyAsync(ctx->d_tile_ids, my_tiles.data(), my_tiles.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+      CU(cudaGraphLaunch(ctx->graph_exec, st));
+      ctx->stats = ctx->graph_stats;
+      replayed = true;
+    }
+  }
   std::vector<int> h_nslots, h_slots;
-  for (size_t first = 0; first < my_tiles.size(); first += tiles_per_pass) {
+  for (size_t first = 0; first < my_tiles.size() && !replayed; first += tiles_per_pass) {
     const int nt = (int)std::min<size_t>(tiles_per_pass, my_tiles.size() - first);
     pb.n_tiles = nt;
     CU(cudaMemcpyAsync(ctx->d_tile_ids, my_tiles.data() + first, nt * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (use_graph) {
+      CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      capturing = true;
+    }
     ctx->stats.passes++;
     const dim3 g_paths((R + 255) / 256, nt), g_shade((QS + 127) / 128, nt);
     timed_begin(ctx, RAYN_K_RAYGEN);
-    k_raygen<<<g_paths, 256, 0, st>>>(ctx->scene, fr, pb);
+    k_raygen<<<g_paths, 256, 0, st>>>(ctx->scene, fr, pb, fold_pre);
     timed_end(ctx, RAYN_K_RAYGEN);
     for (int depth = 0; depth <= mb; ++depth) {
       const Thr thr = make_thr(ctx->scene.cam, depth);
@@ -586,8 +646,9 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
         timed_begin(ctx, RAYN_K_MISC);
         k_scan_live<<<1, SCAN_T, 0, st>>>(pb, ctx->d_batch_prefix, ctx->d_work_ctr);
         timed_end(ctx, RAYN_K_MISC);
-        // fold order of hitable.rs:177-198: runs of spheres as coherent kernels, each SDF as a persistent march
-        int k = 0, first_kernel = 1, n_march = 0;
+        // fold order of hitable.rs:177-198: runs of spheres as coherent kernels, each SDF as a persistent march.  The
+        // spheres before the first SDF were already folded in by the kernel that produced the rays (fold_pre >= 0).
+        int k = fold_pre >= 0 ? fold_pre : 0, first_kernel = fold_pre >= 0 ? 0 : 1, n_march = 0;
         while (k < n_hit || first_kernel) {
           int e = k;
           while (e < n_hit && ctx->scene.hit[e].kind == RAYN_HITABLE_SPHERE) ++e;
@@ -647,7 +708,7 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
           }
         }
         timed_begin(ctx, RAYN_K_SHADE_POST);
-        k_shade_post<<<g_shade, 128, 0, st>>>(ctx->scene, fr, pb, depth);
+        k_shade_post<<<g_shade, 128, 0, st>>>(ctx->scene, fr, pb, depth, fold_pre);
         timed_end(ctx, RAYN_K_SHADE_POST);
       } else {
 #ifdef RAYN_LEGACY_KERNELS
@@ -665,6 +726,20 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
     timed_begin(ctx, RAYN_K_RESOLVE);
     k_resolve<<<dim3((f->tile_w * f->tile_h + wpc - 1) / wpc, nt), wpc * 32, res_smem, st>>>(fr, pb, p_color, p_alpha, p_bg, p_normal, np, wpc);
     timed_end(ctx, RAYN_K_RESOLVE);
+    if (capturing) {
+      cudaGraph_t graph = nullptr;
+      CU(cudaStreamEndCapture(st, &graph));
+      capturing = false;
+      if (ctx->graph_exec) cudaGraphExecDestroy(ctx->graph_exec);
+      ctx->graph_exec = nullptr;
+      const cudaError_t ge = cudaGraphInstantiate(&ctx->graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      CU(ge);
+      ctx->graph_key = key;
+      ctx->graph_stats = ctx->stats;
+      ctx->graph_stats.reserved_ = 1;  // marks "replayed from a captured graph" for callers that look
+      CU(cudaGraphLaunch(ctx->graph_exec, st));
+    }
     CU(cudaGetLastError());
   }
   ctx->job_w = f->width, ctx->job_h = f->height, ctx->job_tw = f->tile_w, ctx->job_th = f->tile_h, ctx->job_spp = spp, ctx->job_nty = fr.nty;

@@ -120,6 +120,16 @@ DM_HD float powi5(float x) {
 }
 
 // ---- double-precision cores --------------------------------------------------------
+// Horner steps and argument reductions use an explicit double fma (one DFMA instead of DMUL + DADD under --fmad=false /
+// -ffp-contract=off; also one rounding less).  Same operation on host and device, so the bits stay identical.
+DM_HD double dfma(double a, double b, double c) {
+#ifdef __CUDA_ARCH__
+  return __fma_rn(a, b, c);
+#else
+  return __builtin_fma(a, b, c);
+#endif
+}
+
 #define DM_LN2_HI 6.93147180369123816490e-01
 #define DM_LN2_LO 1.90821492927058770002e-10
 #define DM_LOG2E 1.4426950408889634
@@ -132,21 +142,21 @@ DM_HD float powi5(float x) {
 // exp for |x| <= ~700; Taylor degree 13 on |r| <= ln2/2
 DM_HD double exp_core(double x) {
   double kf = floor(x * DM_LOG2E + 0.5);
-  double r = (x - kf * DM_LN2_HI) - kf * DM_LN2_LO;
+  double r = dfma(-kf, DM_LN2_LO, dfma(-kf, DM_LN2_HI, x));
   double p = 1.0 / 6227020800.0;
-  p = p * r + 1.0 / 479001600.0;
-  p = p * r + 1.0 / 39916800.0;
-  p = p * r + 1.0 / 3628800.0;
-  p = p * r + 1.0 / 362880.0;
-  p = p * r + 1.0 / 40320.0;
-  p = p * r + 1.0 / 5040.0;
-  p = p * r + 1.0 / 720.0;
-  p = p * r + 1.0 / 120.0;
-  p = p * r + 1.0 / 24.0;
-  p = p * r + 1.0 / 6.0;
-  p = p * r + 0.5;
-  p = p * r + 1.0;
-  p = p * r + 1.0;
+  p = dfma(p, r, 1.0 / 479001600.0);
+  p = dfma(p, r, 1.0 / 39916800.0);
+  p = dfma(p, r, 1.0 / 3628800.0);
+  p = dfma(p, r, 1.0 / 362880.0);
+  p = dfma(p, r, 1.0 / 40320.0);
+  p = dfma(p, r, 1.0 / 5040.0);
+  p = dfma(p, r, 1.0 / 720.0);
+  p = dfma(p, r, 1.0 / 120.0);
+  p = dfma(p, r, 1.0 / 24.0);
+  p = dfma(p, r, 1.0 / 6.0);
+  p = dfma(p, r, 0.5);
+  p = dfma(p, r, 1.0);
+  p = dfma(p, r, 1.0);
   int64_t k = (int64_t)kf;
   return p * i2d((k + 1023) << 52);
 }
@@ -163,42 +173,42 @@ DM_HD double ln_core(double x) {
   double s = (m - 1.0) / (m + 1.0);
   double z = s * s;
   double p = 1.0 / 19.0;
-  p = p * z + 1.0 / 17.0;
-  p = p * z + 1.0 / 15.0;
-  p = p * z + 1.0 / 13.0;
-  p = p * z + 1.0 / 11.0;
-  p = p * z + 1.0 / 9.0;
-  p = p * z + 1.0 / 7.0;
-  p = p * z + 1.0 / 5.0;
-  p = p * z + 1.0 / 3.0;
-  p = p * z + 1.0;
+  p = dfma(p, z, 1.0 / 17.0);
+  p = dfma(p, z, 1.0 / 15.0);
+  p = dfma(p, z, 1.0 / 13.0);
+  p = dfma(p, z, 1.0 / 11.0);
+  p = dfma(p, z, 1.0 / 9.0);
+  p = dfma(p, z, 1.0 / 7.0);
+  p = dfma(p, z, 1.0 / 5.0);
+  p = dfma(p, z, 1.0 / 3.0);
+  p = dfma(p, z, 1.0);
   double ef = (double)e;
-  return ef * DM_LN2_HI + (2.0 * s * p + ef * DM_LN2_LO);
+  return dfma(ef, DM_LN2_HI, dfma(2.0 * s, p, ef * DM_LN2_LO));
 }
 
 // sin and cos of a finite double with |x| < 2^20
 DM_HD void sincos_core(double x, double* sn, double* cs) {
   double kf = floor(x * DM_2OPI + 0.5);
-  double r = (x - kf * DM_PIO2_HI) - kf * DM_PIO2_LO;
+  double r = dfma(-kf, DM_PIO2_LO, dfma(-kf, DM_PIO2_HI, x));
   double z = r * r;
   double ps = -1.0 / 1307674368000.0;
-  ps = ps * z + 1.0 / 6227020800.0;
-  ps = ps * z - 1.0 / 39916800.0;
-  ps = ps * z + 1.0 / 362880.0;
-  ps = ps * z - 1.0 / 5040.0;
-  ps = ps * z + 1.0 / 120.0;
-  ps = ps * z - 1.0 / 6.0;
-  ps = ps * z + 1.0;
+  ps = dfma(ps, z, 1.0 / 6227020800.0);
+  ps = dfma(ps, z, -(1.0 / 39916800.0));
+  ps = dfma(ps, z, 1.0 / 362880.0);
+  ps = dfma(ps, z, -(1.0 / 5040.0));
+  ps = dfma(ps, z, 1.0 / 120.0);
+  ps = dfma(ps, z, -(1.0 / 6.0));
+  ps = dfma(ps, z, 1.0);
   double sr = ps * r;
   double pc = 1.0 / 20922789888000.0;
-  pc = pc * z - 1.0 / 87178291200.0;
-  pc = pc * z + 1.0 / 479001600.0;
-  pc = pc * z - 1.0 / 3628800.0;
-  pc = pc * z + 1.0 / 40320.0;
-  pc = pc * z - 1.0 / 720.0;
-  pc = pc * z + 1.0 / 24.0;
-  pc = pc * z - 0.5;
-  double cr = pc * z + 1.0;
+  pc = dfma(pc, z, -(1.0 / 87178291200.0));
+  pc = dfma(pc, z, 1.0 / 479001600.0);
+  pc = dfma(pc, z, -(1.0 / 3628800.0));
+  pc = dfma(pc, z, 1.0 / 40320.0);
+  pc = dfma(pc, z, -(1.0 / 720.0));
+  pc = dfma(pc, z, 1.0 / 24.0);
+  pc = dfma(pc, z, -(0.5));
+  double cr = dfma(pc, z, 1.0);
   int q = (int)(((int64_t)kf) & 3);
   if (q == 0) {
     *sn = sr;
@@ -222,15 +232,15 @@ DM_HD double atan01_core(double z) {
   z = z / (1.0 + sqrt(1.0 + z * z));
   double w = z * z;
   double p = -1.0 / 19.0;
-  p = p * w + 1.0 / 17.0;
-  p = p * w - 1.0 / 15.0;
-  p = p * w + 1.0 / 13.0;
-  p = p * w - 1.0 / 11.0;
-  p = p * w + 1.0 / 9.0;
-  p = p * w - 1.0 / 7.0;
-  p = p * w + 1.0 / 5.0;
-  p = p * w - 1.0 / 3.0;
-  p = p * w + 1.0;
+  p = dfma(p, w, 1.0 / 17.0);
+  p = dfma(p, w, -(1.0 / 15.0));
+  p = dfma(p, w, 1.0 / 13.0);
+  p = dfma(p, w, -(1.0 / 11.0));
+  p = dfma(p, w, 1.0 / 9.0);
+  p = dfma(p, w, -(1.0 / 7.0));
+  p = dfma(p, w, 1.0 / 5.0);
+  p = dfma(p, w, -(1.0 / 3.0));
+  p = dfma(p, w, 1.0);
   return 4.0 * (z * p);
 }
 
@@ -269,10 +279,10 @@ DM_HD float ln_fast(float x) {
   const float s = (m - 1.0f) / (m + 1.0f);
   const float z = s * s;
   float p = 1.0f / 9.0f;
-  p = p * z + 1.0f / 7.0f;
-  p = p * z + 0.2f;
-  p = p * z + 1.0f / 3.0f;
-  p = p * z + 1.0f;
+  p = dfma(p, z, 1.0f / 7.0f);
+  p = dfma(p, z, 0.2f);
+  p = dfma(p, z, 1.0f / 3.0f);
+  p = dfma(p, z, 1.0f);
   return (float)e * 0.693147180559945f + 2.0f * s * p;
 }
 

@@ -278,6 +278,22 @@ RT_D f3 sphere_center(const RaynHitable& h, float time0) { return seq3(h.center,
 RT_D bool sphere_moves(const RaynHitable& h) {
   return h.kind == RAYN_HITABLE_SPHERE && (h.center_velocity[0] != 0.0f || h.center_velocity[1] != 0.0f || h.center_velocity[2] != 0.0f);
 }
+// Sphere::occluded, sphere.rs:24-46, with the segment's direction and length (lines :25-27: `dir = end - start; dist = dir.mag();
+// dir /= dist`) computed ONCE by the caller: they are the same expressions for every hitable of a segment (TracedSDF::occluded
+// starts with the same three lines, sdf.rs:26-28), so hoisting them changes no bit.
+RT_D float sphere_occluded_seg(const RaynHitable& h, f3 start, f3 dir, float dist, float time0) {
+  f3 oc = start - sphere_center(h, time0);
+  float b = dot(oc, dir);
+  float c = mag_sq(oc) - h.radius * h.radius;
+  float descrim = b * b - c;
+  bool desc_pos = descrim > 0.0f;
+  float desc_sqrt = sqrtf(descrim);
+  float t1 = -b - desc_sqrt;
+  float t2 = -b + desc_sqrt;
+  float mn = dm::min(t1, t2);
+  bool valid = (mn > 0.001f) && (t1 <= dist) && desc_pos;
+  return valid ? 0.0f : 1.0f;
+}
 RT_D float sphere_occluded(const RaynHitable& h, f3 start, f3 end, float time0) {  // :24-46
   f3 dir = end - start;
   float dist = mag(dir);

@@ -10,7 +10,9 @@
 //     term[g]    u32     kind<<30 | depth<<20 | slot at termination (integrator.rs:178-203)
 //   per tile, index queues (the "ray queue": what is compacted and partitioned is a 4-byte id):
 //     q_live[ts*R + i]    live path ids in packet order           (film.rs:608-625)
-//     q_key[ts*R + i]     object hit by q_live[i], -1 = nothing   (hitable.rs:203-209)
+//     q_key[ts*R + id]    object hit by path id at this depth, -1 = nothing (hitable.rs:203-209); indexed by PATH so that
+//                         the kernel that produces a ray (raygen, shade_post) can already run the analytic spheres
+//                         that precede the first SDF in the fold order
 //     q_shade[ts*QS + s]  shading slots: per-object bins, each padded to x4 with -1
 //                         (hitable.rs:94-133)
 //   g = ts*R + id, id = (xl*th + yl)*spp + sample  — the reference's raygen order
@@ -117,10 +119,29 @@ RT_D void warp_add(unsigned long long* ctr, int v) {
   if ((threadIdx.x & 31) == 0 && v) atomicAdd(ctr, (unsigned long long)v);
 }
 
+// The head of the closest-hit fold (hitable.rs:177-198): t_max = 2 * WORLD_RADIUS (film.rs:556), then the analytic spheres
+// [0, pre_n) that precede the first SDF hitable, in insertion order.  Run by the kernel that PRODUCES the ray (origin and
+// direction are in registers there), which removes one gather of every live ray per depth.  Static spheres only: a moving
+// sphere is evaluated at the time of lane 0 of the extend packet, which is not known before compaction (k_extend_spheres
+// handles that case).
+RT_D void fold_head(const DevScene& sc, int pre_n, f3 o, f3 d, float* closest, int* id) {
+  float c = sc.rc.world_radius * 2.0f;
+  int best = -1;
+  for (int k = 0; k < pre_n; ++k) {
+    const float t = sphere_hit(sc.hit[k], o, d, c, 0.0f);
+    if (t < c) {
+      c = t;
+      best = k;
+    }
+  }
+  *closest = c;
+  *id = best;
+}
+
 // ------------------------------------------------------------------------------------------
 // K1 raygen: film.rs:456-529 + sample_uv :695-709 + camera.rs get_rays
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ DevScene sc, const DevFrame fr, const PassBufs pb) {
+__global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ DevScene sc, const DevFrame fr, const PassBufs pb, const int pre_n) {
   const int ts = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const TileGeom tg = tile_geom(fr, pb.tile_ids[ts]);
@@ -142,8 +163,12 @@ __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ DevScene
   f3 ro, rd;
   camera_ray(sc.cam, u, v, ls0, ls1, time0, &ro, &rd);
   const size_t g = (size_t)ts * pb.R + i;
+  float closest = 0.0f;
+  int hit_id = -1;
+  if (pre_n >= 0) fold_head(sc, pre_n, ro, rd, &closest, &hit_id);  // pre_n < 0: k_extend_spheres starts the fold (moving spheres)
   pb.o_time[g] = make_float4(ro.x, ro.y, ro.z, time);
-  pb.d_t[g] = make_float4(rd.x, rd.y, rd.z, 0.0f);
+  pb.d_t[g] = make_float4(rd.x, rd.y, rd.z, closest);
+  pb.q_key[g] = hit_id;
   pb.rad[g] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   pb.thr[g] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
   pb.nrm0[g] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(0u));
@@ -165,14 +190,15 @@ __global__ void __launch_bounds__(BIN_T) k_bin(const PassBufs pb, const int n_hi
   __shared__ int start[RAYN_MAX_HITABLES + 1];
   __shared__ int running[2][RAYN_MAX_HITABLES];
   __shared__ int wcnt[2][NW][RAYN_MAX_HITABLES];
-  const int* __restrict__ qk = pb.q_key + (size_t)ts * pb.R;
+  const int* __restrict__ qk = pb.q_key + (size_t)ts * pb.R;  // per path
   const int* __restrict__ ql = pb.q_live + (size_t)ts * pb.R;
   int* __restrict__ qs = pb.q_shade + (size_t)ts * pb.QS;
   if (tid < RAYN_MAX_HITABLES) cnt[tid] = 0;
+  if (tid == 0 && n) atomicAdd(pb.counters + CNT_EXTEND_RAYS, (unsigned long long)n);  // rays through the closest-hit stage
   __syncthreads();
   for (int base = 0; base < n; base += BIN_T) {  // pass A: per-object counts
     const int i = base + tid;
-    const int key = i < n ? qk[i] : -1;
+    const int key = i < n ? qk[ql[i]] : -1;
     const unsigned m = __match_any_sync(0xffffffffu, key);
     if (key >= 0 && (m & ((1u << lane) - 1)) == 0) atomicAdd(&cnt[key], __popc(m));
   }
@@ -193,8 +219,8 @@ __global__ void __launch_bounds__(BIN_T) k_bin(const PassBufs pb, const int n_hi
   int buf = 0;
   for (int base = 0; base < n; base += BIN_T, buf ^= 1) {
     const int i = base + tid;
-    const int key = i < n ? qk[i] : -1;
     const int id = i < n ? ql[i] : -1;
+    const int key = i < n ? qk[id] : -1;
     unsigned mine = 0;
     for (int k = 0; k < n_hit; ++k) {
       const unsigned b = __ballot_sync(0xffffffffu, key == k);
@@ -279,7 +305,7 @@ __global__ void __launch_bounds__(256) k_extend_spheres(const __grid_constant__ 
     const float4 o4 = pb.o_time[g], d4 = pb.d_t[g];
     const f3 o = mk3(o4.x, o4.y, o4.z), d = mk3(d4.x, d4.y, d4.z);
     float closest = init ? sc.rc.world_radius * 2.0f : d4.w;  // film.rs:556
-    int id = init ? -1 : pb.q_key[q];
+    int id = init ? -1 : pb.q_key[g];
     // packets of the extend stage are 4 consecutive live rays (film.rs:612-624); a moving sphere is evaluated at lane 0's time
     float time0 = o4.w;
     if (moving && (i & 3)) time0 = pb.o_time[(size_t)ts * pb.R + pb.q_live[(size_t)ts * pb.R + (i & ~3)]].w;
@@ -291,9 +317,8 @@ __global__ void __launch_bounds__(256) k_extend_spheres(const __grid_constant__ 
       }
     }
     pb.d_t[g].w = closest;
-    pb.q_key[q] = id;
+    pb.q_key[g] = id;
   }
-  if (init) warp_add(pb.counters + CNT_EXTEND_RAYS, act ? 1 : 0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -308,8 +333,11 @@ __global__ void __launch_bounds__(256) k_extend_spheres(const __grid_constant__ 
 // t + key (8 B) when this SDF is the new closest hit.
 // ------------------------------------------------------------------------------------------
 #define EXT_T 128
+#ifndef RAYN_MARCH_OCC
+#define RAYN_MARCH_OCC 8  // resident CTAs per SM the march kernels are compiled for (register budget 65536 / (128 * OCC))
+#endif
 template <int V>
-__global__ void __launch_bounds__(EXT_T, 8) k_extend_march(const __grid_constant__ DevScene sc, const PassBufs pb, const Thr thr,
+__global__ void __launch_bounds__(EXT_T, RAYN_MARCH_OCC) k_extend_march(const __grid_constant__ DevScene sc, const PassBufs pb, const Thr thr,
                                                           const int hk, const int* __restrict__ batch_prefix, int* __restrict__ work_ctr) {
   const SdfK k = make_sdfk(sc.hit[hk], sc.one);  // fractal constants: kernel-parameter bank -> registers, once
   const int lane = threadIdx.x & 31;
@@ -320,7 +348,7 @@ __global__ void __launch_bounds__(EXT_T, 8) k_extend_march(const __grid_constant
   const int n_batches = batch_prefix[pb.n_tiles];
   bool have0 = false, have1 = false, first0 = false, first1 = false, exhausted = false;
   float2 ox = splat2(0.0f), oy = ox, oz = ox, dx = ox, dy = ox, dz = ox, t = ox, closest = ox;
-  int q0 = 0, q1 = 0, g0 = 0, g1 = 0, steps0 = 0, steps1 = 0, evals = 0, bulb_iters = 0;
+  int g0 = 0, g1 = 0, steps0 = 0, steps1 = 0, evals = 0, bulb_iters = 0;
   int cur_base = 0, cur_pos = 0, cur_end = 0;
   while (true) {
     __syncwarp();
@@ -347,15 +375,13 @@ __global__ void __launch_bounds__(EXT_T, 8) k_extend_march(const __grid_constant
       const int n0 = __popc(idle0);
       const int rank0 = __popc(idle0 & lt), rank1 = n0 + __popc(idle1 & lt);
       if (!have0 && rank0 < avail) {
-        q0 = cur_base + cur_pos + rank0;
-        g0 = cur_base + pb.q_live[q0];
+        g0 = cur_base + pb.q_live[cur_base + cur_pos + rank0];
         const float4 o4 = pb.o_time[g0], d4 = pb.d_t[g0];
         ox.x = o4.x, oy.x = o4.y, oz.x = o4.z, dx.x = d4.x, dy.x = d4.y, dz.x = d4.z, closest.x = d4.w;
         first0 = have0 = true;
       }
       if (!have1 && rank1 < avail) {
-        q1 = cur_base + cur_pos + rank1;
-        g1 = cur_base + pb.q_live[q1];
+        g1 = cur_base + pb.q_live[cur_base + cur_pos + rank1];
         const float4 o4 = pb.o_time[g1], d4 = pb.d_t[g1];
         ox.y = o4.x, oy.y = o4.y, oz.y = o4.z, dx.y = d4.x, dy.y = d4.y, dz.y = d4.z, closest.y = d4.w;
         first1 = have1 = true;
@@ -372,52 +398,41 @@ __global__ void __launch_bounds__(EXT_T, 8) k_extend_march(const __grid_constant
     if (!have0) px.x = 100.0f, py.x = 0.0f, pz.x = 0.0f;
     if (!have1) px.y = 100.0f, py.y = 0.0f, pz.y = 0.0f;
     const float2 dd = sdf_dist2<V>(k, px, py, pz, bulb_iters);
-    if (have0) {
-      ++evals;
-      bool end;
-      if (first0) {
-        t.x = dd.x, steps0 = 0, first0 = false;
-        end = t.x != t.x;  // NaN start: returns NaN, the caller's t < closest is false (hitable.rs:190)
-      } else {
-        const bool hit = dm::abs(dd.x) < dm::max(c0, c1 * thr.at(t.x));
-        if (hit || t.x > closest.x) {
-          end = true;
-        } else {
-          t.x = t.x + dd.x;
-          ++steps0;
-          end = (t.x != t.x) || steps0 >= max_marches;  // a NaN can never satisfy hit/gt again: marches to exhaustion, returns NaN
+    // per-slot march step, branch-free over `first` so that all busy lanes of the warp run ONE code path:
+    //   first evaluation (sdf.rs:60-61): t = dist(origin); a NaN start ends the march (the caller's t < closest is false);
+    //   later (sdf.rs:65-80): stop on hit or t > t_max, else t += dist; a NaN t can never satisfy hit/gt again and the
+    //   reference marches it to exhaustion and returns NaN - ending at once returns the same NaN.
+    evals += (have0 ? 1 : 0) + (have1 ? 1 : 0);
+    {
+      const bool stop = !first0 && ((dm::abs(dd.x) < dm::max(c0, c1 * thr.at(t.x))) || t.x > closest.x);
+      const float tn = first0 ? dd.x : t.x + dd.x;
+      const int sn = first0 ? 0 : steps0 + 1;
+      if (have0) {
+        if (!stop) t.x = tn, steps0 = sn;
+        first0 = false;
+        if (stop || (tn != tn) || sn >= max_marches) {
+          if (t.x < closest.x) {  // hitable.rs:190-193
+            pb.d_t[g0].w = t.x;
+            pb.q_key[g0] = hk;
+          }
+          have0 = false;
         }
-      }
-      if (end) {
-        if (t.x < closest.x) {  // hitable.rs:190-193
-          pb.d_t[g0].w = t.x;
-          pb.q_key[q0] = hk;
-        }
-        have0 = false;
       }
     }
-    if (have1) {
-      ++evals;
-      bool end;
-      if (first1) {
-        t.y = dd.y, steps1 = 0, first1 = false;
-        end = t.y != t.y;
-      } else {
-        const bool hit = dm::abs(dd.y) < dm::max(c0, c1 * thr.at(t.y));
-        if (hit || t.y > closest.y) {
-          end = true;
-        } else {
-          t.y = t.y + dd.y;
-          ++steps1;
-          end = (t.y != t.y) || steps1 >= max_marches;
+    {
+      const bool stop = !first1 && ((dm::abs(dd.y) < dm::max(c0, c1 * thr.at(t.y))) || t.y > closest.y);
+      const float tn = first1 ? dd.y : t.y + dd.y;
+      const int sn = first1 ? 0 : steps1 + 1;
+      if (have1) {
+        if (!stop) t.y = tn, steps1 = sn;
+        first1 = false;
+        if (stop || (tn != tn) || sn >= max_marches) {
+          if (t.y < closest.y) {
+            pb.d_t[g1].w = t.y;
+            pb.q_key[g1] = hk;
+          }
+          have1 = false;
         }
-      }
-      if (end) {
-        if (t.y < closest.y) {
-          pb.d_t[g1].w = t.y;
-          pb.q_key[q1] = hk;
-        }
-        have1 = false;
       }
     }
   }
@@ -614,16 +629,17 @@ __global__ void __launch_bounds__(128, 8) k_shade_pre(const __grid_constant__ De
           // a contribution that is (+-0 | NaN) in every channel is the same bits for visibility 0 and 1
           const bool irrelevant = (lc.c.x == 0.0f || lc.c.x != lc.c.x) && (lc.c.y == 0.0f || lc.c.y != lc.c.y) && (lc.c.z == 0.0f || lc.c.z != lc.c.z);
           if (irrelevant) continue;
+          // direction and length of the segment: the first three lines of every Hitable::occluded (sphere.rs:25-27, sdf.rs:26-28)
+          f3 dir = lc.end_point - lc.start;
+          const float max_dist = mag(dir);
+          dir = dir / max_dist;
           float v = 1.0f;  // analytic spheres first: product of {0,1} factors (hitable.rs:164-168)
           for (int k = 0; k < sc.n_hit && v != 0.0f; ++k)
-            if (sc.hit[k].kind == RAYN_HITABLE_SPHERE) v = sphere_occluded(sc.hit[k], lc.start, lc.end_point, time0);
+            if (sc.hit[k].kind == RAYN_HITABLE_SPHERE) v = sphere_occluded_seg(sc.hit[k], lc.start, dir, max_dist, time0);
           if (v == 0.0f) {
             vis &= ~(1u << bit);
             continue;
           }
-          f3 dir = lc.end_point - lc.start;  // TracedSDF::occluded prologue, sdf.rs:26-28
-          const float max_dist = mag(dir);
-          dir = dir / max_dist;
           int j = 0;  // SDF ordinal
           for (int k = 0; k < sc.n_hit; ++k)
             if (sc.hit[k].kind != RAYN_HITABLE_SPHERE) {
@@ -654,7 +670,7 @@ __global__ void __launch_bounds__(128, 8) k_shade_pre(const __grid_constant__ De
 #define SHD_T 128
 #define SHD_BATCH 128
 template <int V>
-__global__ void __launch_bounds__(SHD_T, 8) k_shadow(const __grid_constant__ DevScene sc, const PassBufs pb, const int hk, const int j,
+__global__ void __launch_bounds__(SHD_T, RAYN_MARCH_OCC) k_shadow(const __grid_constant__ DevScene sc, const PassBufs pb, const int hk, const int j,
                                                     int* __restrict__ work_ctr) {
   const SdfK k = make_sdfk(sc.hit[hk], sc.one);
   const int lane = threadIdx.x & 31;
@@ -709,37 +725,29 @@ __global__ void __launch_bounds__(SHD_T, 8) k_shadow(const __grid_constant__ Dev
     if (!have0) px.x = 100.0f, py.x = 0.0f, pz.x = 0.0f;
     if (!have1) px.y = 100.0f, py.y = 0.0f, pz.y = 0.0f;
     const float2 dd = sdf_dist2<V>(k, px, py, pz, bulb_iters);
-    if (have0) {
-      ++evals;
-      bool done;
-      if (first0) {
-        t.x = dd.x, first0 = false, steps0 = 0;
-        done = (t.x != t.x) || (t.x > max_dist.x);
-      } else if (dm::abs(dd.x) < dm::max(oc0, oc1 * t.x)) {
-        atomicAnd(pb.vis + ((unsigned)own0 >> 4), ~(1u << (own0 & 15)));  // occluded
-        done = true;
-      } else {
-        t.x = t.x + dd.x;
-        ++steps0;
-        done = (t.x != t.x) || steps0 >= max_vis || (t.x > max_dist.x);
+    // per-slot step of TracedSDF::occluded, branch-free over `first` (see k_extend_march):
+    //   first (sdf.rs:30-36): t = dist(start);   later (:40-55): occluded when |dist| < max(1e-4 S, 1e-5 S t), else t += dist;
+    //   the march ends unoccluded when t is NaN, exceeds max_dist, or after MAX_VIS_MARCHES steps.
+    evals += (have0 ? 1 : 0) + (have1 ? 1 : 0);
+    {
+      const bool occ = !first0 && (dm::abs(dd.x) < dm::max(oc0, oc1 * t.x));
+      const float tn = first0 ? dd.x : t.x + dd.x;
+      const int sn = first0 ? 0 : steps0 + 1;
+      if (have0) {
+        if (occ) atomicAnd(pb.vis + ((unsigned)own0 >> 4), ~(1u << (own0 & 15)));
+        t.x = tn, steps0 = sn, first0 = false;
+        if (occ || (tn != tn) || sn >= max_vis || tn > max_dist.x) have0 = false;
       }
-      if (done) have0 = false;
     }
-    if (have1) {
-      ++evals;
-      bool done;
-      if (first1) {
-        t.y = dd.y, first1 = false, steps1 = 0;
-        done = (t.y != t.y) || (t.y > max_dist.y);
-      } else if (dm::abs(dd.y) < dm::max(oc0, oc1 * t.y)) {
-        atomicAnd(pb.vis + ((unsigned)own1 >> 4), ~(1u << (own1 & 15)));
-        done = true;
-      } else {
-        t.y = t.y + dd.y;
-        ++steps1;
-        done = (t.y != t.y) || steps1 >= max_vis || (t.y > max_dist.y);
+    {
+      const bool occ = !first1 && (dm::abs(dd.y) < dm::max(oc0, oc1 * t.y));
+      const float tn = first1 ? dd.y : t.y + dd.y;
+      const int sn = first1 ? 0 : steps1 + 1;
+      if (have1) {
+        if (occ) atomicAnd(pb.vis + ((unsigned)own1 >> 4), ~(1u << (own1 & 15)));
+        t.y = tn, steps1 = sn, first1 = false;
+        if (occ || (tn != tn) || sn >= max_vis || tn > max_dist.y) have1 = false;
       }
-      if (done) have1 = false;
     }
   }
   warp_add(pb.counters + CNT_EVALS_SHADOW, evals);
@@ -747,7 +755,7 @@ __global__ void __launch_bounds__(SHD_T, 8) k_shadow(const __grid_constant__ Dev
 }
 
 __global__ void __launch_bounds__(128, 8) k_shade_post(const __grid_constant__ DevScene sc, const DevFrame fr, const PassBufs pb,
-                                                       const int depth) {
+                                                       const int depth, const int pre_n) {
   const int ts = blockIdx.y;
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const int nslots = pb.n_slots[ts];
@@ -813,8 +821,12 @@ __global__ void __launch_bounds__(128, 8) k_shade_post(const __grid_constant__ D
     } else {
       const f3 no = sp.point + sp.normal * dm::signum(dot(sp.normal, se.wi)) * sp.offset_by;
       if (!any_nan(new_throughput)) throughput = new_throughput;
+      float closest = 0.0f;
+      int hit_id = -1;
+      if (pre_n >= 0) fold_head(sc, pre_n, no, se.wi, &closest, &hit_id);  // head of the next depth's closest-hit fold
       pb.o_time[g] = make_float4(no.x, no.y, no.z, sp.time);
-      pb.d_t[g] = make_float4(se.wi.x, se.wi.y, se.wi.z, 0.0f);
+      pb.d_t[g] = make_float4(se.wi.x, se.wi.y, se.wi.z, closest);
+      pb.q_key[g] = hit_id;
       pb.rad[g] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
       pb.thr[g] = make_float4(throughput.x, throughput.y, throughput.z, 0.0f);
     }

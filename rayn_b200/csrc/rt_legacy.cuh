@@ -29,9 +29,8 @@ __global__ void __launch_bounds__(128) k_extend(const __grid_constant__ DevScene
     int obj;
     closest_hit(sc, mk3(o4.x, o4.y, o4.z), mk3(d4.x, d4.y, d4.z), thr, &t, &obj, &evals);
     pb.d_t[g].w = t;
-    pb.q_key[q] = obj;
+    pb.q_key[g] = obj;
   }
-  warp_add(pb.counters + CNT_EXTEND_RAYS, act ? 1 : 0);
   warp_add(pb.counters + CNT_EVALS_EXTEND, evals);
 }
 

@@ -113,7 +113,7 @@ def test_limits_are_reported_not_crashed():
         c, inp = small_config(1, (16, 16), 1, 1)
         r.upload_scene(c["world"], c["camera"])
         big = PathTracingIntegrator(1, 2)
-        huge = FrameInputs(16, 16, 1100, big)  # 16*16*4400 spp > 2^20 slot keys
+        huge = FrameInputs(16, 16, 4200, big)  # 16*16*16800 spp > 2^22 slot keys (and > the 16384 spp the film resolve stages)
         with pytest.raises(L.RaynError) as e:
             r.render_host(huge, (16, 16), big, TR)
         assert e.value.code == L.RAYN_ERR_UNSUPPORTED
@@ -128,6 +128,66 @@ def test_limits_are_reported_not_crashed():
         assert e.value.code == L.RAYN_ERR_UNSUPPORTED
     finally:
         r.close()
+
+
+def test_small_frames_replay_a_cuda_graph_and_stay_bit_exact(oracle):
+    """Launch-bound frames (config 1 geometry) are captured into a CUDA graph once and replayed; the film must not depend on
+    whether the kernels were launched directly (RAYN_FLAG_NO_GRAPH), captured, or replayed, and a changed scene or frame must
+    invalidate the captured graph."""
+    c, inp = small_config(1, (64, 64), 1, 2)
+    o, _ = oracle.render(c["world"], c["camera"], inp, (16, 16), c["integrator"], TR)
+    direct = Renderer(0, flags=L.FLAG_NO_GRAPH)
+    r = Renderer(0)
+    try:
+        direct.upload_scene(c["world"], c["camera"])
+        d = direct.render_host(inp, (16, 16), c["integrator"], TR)
+        assert direct.stats().reserved_ == 0
+        r.upload_scene(c["world"], c["camera"])
+        # device-resident inputs and planes, so that every pointer baked into the graph stays the same between frames
+        import torch
+        dev = torch.device("cuda", 0)
+        ins = [torch.from_numpy(a).to(dev) for a in inp.arrays()]
+        from rayn_b200.dist import device_frame_desc
+        npx = 64 * 64
+        store = torch.zeros(10 * npx, dtype=torch.float32, device=dev)
+        planes = L.RaynFilmPlanes(store[:3 * npx].data_ptr(), store[3 * npx:4 * npx].data_ptr(), store[4 * npx:7 * npx].data_ptr(), store[7 * npx:].data_ptr(), L.MEM_DEVICE)
+        fd = device_frame_desc(ins, 64, 64, (16, 16), c["samples"], c["integrator"], 1, TR, (inp.sets_1d, inp.sets_2d))
+        launches = []
+        for i in range(3):
+            store.zero_()
+            torch.cuda.synchronize()
+            r.render(fd, planes)
+            st = r.stats()
+            launches.append(st.launches)
+            assert st.reserved_ == 1, "frame was not served by the captured graph"
+            got = store.cpu().numpy()
+            for ch, (a, b) in zip(CH, ((0, 3), (3, 4), (4, 7), (7, 10))):
+                assert_bit_equal(got[a * npx:b * npx], o[ch], f"graph frame {i} {ch}")
+                assert_bit_equal(got[a * npx:b * npx], d[ch], f"graph vs direct {i} {ch}")
+        assert launches[0] == launches[1] == launches[2] > 0
+        # another scene through the same context: the key changes, the graph is rebuilt, results follow the new scene
+        c3, inp3 = small_config(3, (64, 64), 1, 2)
+        r.upload_scene(c3["world"], c3["camera"])
+        g3 = r.render_host(inp3, (16, 16), c3["integrator"], TR)
+        o3, _ = oracle.render(c3["world"], c3["camera"], inp3, (16, 16), c3["integrator"], TR)
+        for ch in CH:
+            assert_bit_equal(g3[ch], o3[ch], f"after scene change {ch}")
+    finally:
+        direct.close()
+        r.close()
+
+
+def test_very_high_spp_tile_resolves_bit_exact(renderer, oracle):
+    """4400 spp per pixel (more than the 4096 spp a weak-scaled 8-GPU config 3 frame uses): 1.1 M paths per tile, the film
+    resolve orders 8192 keys per pixel in shared memory with 2 warps per CTA.  Scene with two objects so slots interleave."""
+    c, _ = small_config(1, (16, 16), 1, 2)
+    integ = PathTracingIntegrator(2, 2)
+    inp = FrameInputs(16, 16, 1100, integ)
+    renderer.upload_scene(c["world"], c["camera"])
+    g = renderer.render_host(inp, (16, 16), integ, TR)
+    o, _ = oracle.render(c["world"], c["camera"], inp, (16, 16), integ, TR)
+    for ch in CH:
+        assert_bit_equal(g[ch], o[ch], f"4400 spp {ch}")
 
 
 def test_film_postprocess_bit_exact_and_save_to(renderer, oracle, tmp_path):
