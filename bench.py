@@ -416,12 +416,14 @@ class Bench:
         if "extend" in per:
             per["extend"].update(rays=int(ts.extend_rays), sdf_evals=int(ts.sdf_evals_extend),
                                  iterations_per_eval=(ts.bulb_iters_extend / max(ts.sdf_evals_extend, 1)) if is_bulb else iters,
+                                 march_slots_busy=ts.sdf_evals_extend / max(64.0 * ts.march_trips_extend, 1.0),
                                  hbm_gbs_algorithmic=ts.extend_rays * ALG_BYTES_EXTEND / max(ext_s, 1e-12) / 1e9,
                                  fp32_tflops_algorithmic=flops(ts.sdf_evals_extend, ts.bulb_iters_extend) / max(ext_s, 1e-12) / 1e12)
         if "shadow" in per:
             n_seg = int(ts.shadow_rays)  # light samples prepared; the segments actually marched are fewer (exact pre-filters)
             per["shadow"].update(shadow_rays=n_seg, sdf_evals=int(ts.sdf_evals_shadow),
                                  iterations_per_eval=(ts.bulb_iters_shadow / max(ts.sdf_evals_shadow, 1)) if is_bulb else iters,
+                                 march_slots_busy=ts.sdf_evals_shadow / max(64.0 * ts.march_trips_shadow, 1.0),
                                  hbm_gbs_algorithmic=n_seg * ALG_BYTES_SHADOW / max(shd_s, 1e-12) / 1e9,
                                  fp32_tflops_algorithmic=flops(ts.sdf_evals_shadow, ts.bulb_iters_shadow) / max(shd_s, 1e-12) / 1e12)
         if "normals" in per:

@@ -222,6 +222,7 @@ typedef struct RaynConfig {
 #define RAYN_FLAG_SIMPLE_MARCH 2 /* TEST BUILD ONLY (-DRAYN_LEGACY_KERNELS, librayn_b200_legacy.so): round-1 v0
                                     one-thread-per-ray kernels; RAYN_ERR_UNSUPPORTED in the product library */
 
+#define RAYN_FLAG_NO_DIV3 32     /* never select the three-operation sphere-fold division (see rayn_b200_debug_sdf_variant) */
 #define RAYN_FLAG_NO_GRAPH 16    /* launch every kernel directly; by default small single-pass frames (launch bound) are
                                     captured once into a CUDA graph and replayed with one launch                */
 
@@ -241,7 +242,9 @@ typedef struct RaynStats {
   int64_t sdf_evals_normals;        /* SDF dist() evaluations of get_shading_info (4 per SDF shading lane) */
   int64_t bulb_iters_extend;        /* Mandelbulb iterations actually run inside K2 (data dependent)       */
   int64_t bulb_iters_shadow;        /* ... inside K5                                                       */
-  int64_t reserved_;                /* 1 when the last frame was replayed from the captured CUDA graph     */
+  int64_t reserved_;                /* 1 when the last frame ran as ONE CUDA-graph launch (captured or replayed) */
+  int64_t march_trips_extend;       /* warp-level distance-evaluation trips of K2: sdf_evals_extend / (64 * trips) = busy march slots */
+  int64_t march_trips_shadow;       /* ... of K5                                                                                      */
 } RaynStats;
 
 /* indices into kernel_ms / kernel_launches */
@@ -371,7 +374,8 @@ int32_t rayn_b200_kat_detmath(RaynContext* ctx, int32_t op, int64_t n, const flo
 int32_t rayn_b200_kat_sdf_dist(RaynContext* ctx, const RaynHitable* sdf, int64_t n,
                                const float* points3, float* out);
 /* the same through the packed two-point estimator the march kernels run (rt_sdf2.cuh); variant < 0 = the one the
- * scheduler would pick for this hitable, else force 0 generic Mandelbox / 1 12-iteration fast / 2 n-iteration fast / 3 Mandelbulb */
+ * scheduler would pick for this hitable, else force 0 generic Mandelbox / 1 12-iteration fast / 2 n-iteration fast / 3 Mandelbulb /
+ * 4, 5 = 1, 2 with the three-operation sphere-fold division (RAYN_ERR_INVALID_ARG unless its exhaustive check passes here) */
 int32_t rayn_b200_kat_sdf_dist2(RaynContext* ctx, const RaynHitable* sdf, int32_t variant, int64_t n,
                                 const float* points3, float* out);
 /* Newton division of the Mandelbox sphere fold vs IEEE division: number of x among the n consecutive floats starting
@@ -403,6 +407,12 @@ int32_t rayn_b200_kat_light_sample_volume(RaynContext* ctx, const RaynLight* lig
 int32_t rayn_b200_kat_bsdf(RaynContext* ctx, const RaynMaterial* mat, int64_t n, const float* normals3,
                            const float* wo3, const float* s1d, const float* u4, float* out_wi3,
                            float* out_f3, float* out_pdf, float* out_feval3);
+
+/* Which march-kernel specialisation upload_scene selected for hitable `hitable_index` of the current scene: -1 analytic sphere,
+ * 0 generic Mandelbox, 1 / 2 packed Mandelbox (12 / n iterations), 3 Mandelbulb, 4 / 5 = 1 / 2 with the three-operation
+ * sphere-fold division, which upload_scene selects only after dividing by EVERY float in [min_rad_sq, fixed_rad_sq] on this
+ * device and finding all quotients equal to IEEE division; -2 = bad index / no scene                                      */
+int32_t rayn_b200_debug_sdf_variant(const RaynContext* ctx, int32_t hitable_index);
 
 /* Packet-order debugging: when enabled, render_frame records for every depth
  * and tile the shading queue (path id per slot, -1 = padding) into an internal host log. */

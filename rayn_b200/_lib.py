@@ -38,7 +38,7 @@ CAMERA_PINHOLE, CAMERA_THINLENS, CAMERA_ORTHOGRAPHIC = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 POST_COLOR_PLUS_BACKGROUND, POST_COLOR_ALPHA, POST_COLOR_ONLY, POST_BACKGROUND, POST_WORLD_NORMAL, POST_ALPHA = range(6)
 POST_BYTES = (3, 4, 3, 3, 3, 1)
-FLAG_TIMING, FLAG_SIMPLE_MARCH, FLAG_NO_GRAPH = 1, 2, 16
+FLAG_TIMING, FLAG_SIMPLE_MARCH, FLAG_NO_GRAPH, FLAG_NO_DIV3 = 1, 2, 16, 32
 STAT_KERNELS = 12
 KERNEL_NAMES = ["raygen", "extend", "bin", "shade_pre", "shadow", "shade_post", "compact", "resolve", "misc", "normals", "extend_spheres", "gather"]
 
@@ -108,7 +108,8 @@ class RaynStats(C.Structure):
                 ("shade_lanes", i64), ("shadow_rays", i64), ("sdf_evals_extend", i64),
                 ("sdf_evals_shadow", i64), ("kernel_ms", f32 * STAT_KERNELS),
                 ("kernel_launches", i64 * STAT_KERNELS), ("total_ms", f32), ("sdf_evals_normals", i64),
-                ("bulb_iters_extend", i64), ("bulb_iters_shadow", i64), ("reserved_", i64)]
+                ("bulb_iters_extend", i64), ("bulb_iters_shadow", i64), ("reserved_", i64),
+                ("march_trips_extend", i64), ("march_trips_shadow", i64)]
 
 
 # name -> (restype, argtypes); this table is also what the CPU test checks the header against
@@ -150,6 +151,7 @@ SYMBOLS = {
     "rayn_b200_kat_light_sample": (i32, [C.c_void_p, C.POINTER(RaynLight), i64, fp, fp, fp, fp, fp]),
     "rayn_b200_kat_light_sample_volume": (i32, [C.c_void_p, C.POINTER(RaynLight), i64, fp, fp, fp, fp, fp, fp]),
     "rayn_b200_kat_bsdf": (i32, [C.c_void_p, C.POINTER(RaynMaterial), i64, fp, fp, fp, fp, fp, fp, fp, fp]),
+    "rayn_b200_debug_sdf_variant": (i32, [C.c_void_p, i32]),
     "rayn_b200_debug_enable_queue_log": (i32, [C.c_void_p, i32]),
     "rayn_b200_debug_read_queue_log": (i64, [C.c_void_p, C.POINTER(i32), i64]),
 }

@@ -73,6 +73,9 @@ struct RaynContext {
   int* d_work_ctr = nullptr;      // [WC_TOTAL] global work counters of the persistent kernels
   int n_sm = 148;
   int occ_ext[SDFV_COUNT], occ_shd[SDFV_COUNT];
+  int sdf_var[RAYN_MAX_HITABLES];  // march-kernel variant of every SDF hitable of the uploaded scene (rt_sdf2.cuh::sdf_variant)
+  struct Div3Check { float min_r2, fixed_r2; bool ok; };
+  std::vector<Div3Check> div3_cache;  // exhaustive fastdiv2_3 checks already run on this device
   // staging for host-space inputs / outputs
   float *d_s1 = nullptr, *d_s2 = nullptr, *d_scr = nullptr, *d_fis = nullptr;
   size_t cap_s1 = 0, cap_s2 = 0, cap_scr = 0;
@@ -269,6 +272,8 @@ struct DevTmp {
     case SDFV_BOX_12_FAST: { constexpr int V = SDFV_BOX_12_FAST; STMT; } break;       \
     case SDFV_BOX_N_FAST: { constexpr int V = SDFV_BOX_N_FAST; STMT; } break;         \
     case SDFV_BULB: { constexpr int V = SDFV_BULB; STMT; } break;                     \
+    case SDFV_BOX_12_DIV3: { constexpr int V = SDFV_BOX_12_DIV3; STMT; } break;       \
+    case SDFV_BOX_N_DIV3: { constexpr int V = SDFV_BOX_N_DIV3; STMT; } break;         \
     default: { constexpr int V = SDFV_BOX_GENERIC; STMT; } break;                     \
   }
 
@@ -405,6 +410,32 @@ static int32_t validate_scene(RaynContext* ctx, const RaynSceneDesc* s) {
   return RAYN_OK;
 }
 
+// Is the three-operation sphere-fold division (rt_sdf2.cuh::fastdiv2_3) equal to IEEE division for EVERY divisor this
+// Mandelbox can produce?  The divisor is clamp(r2, min_r2, fixed_r2), so the candidates are the floats of that interval: all of
+// them are divided on the device, once per (min_r2, fixed_r2) pair and context (~0.1 ms per 10^8 divisors).
+static bool div3_verified(RaynContext* ctx, const RaynHitable& h) {
+  if (!sdf_box_fast_ok(h)) return false;
+  for (const auto& c : ctx->div3_cache)
+    if (c.min_r2 == h.min_rad_sq && c.fixed_r2 == h.fixed_rad_sq) return c.ok;
+  bool ok = false;
+  uint32_t lo, hi;
+  memcpy(&lo, &h.min_rad_sq, 4);
+  memcpy(&hi, &h.fixed_rad_sq, 4);
+  if (hi >= lo && cudaSetDevice(ctx->device) == cudaSuccess) {  // positive floats order like their bit patterns
+    const unsigned long long n = (unsigned long long)(hi - lo) + 1ull;
+    unsigned long long bad = 1;
+    if (cudaMemsetAsync(ctx->d_kat, 0, sizeof(unsigned long long), ctx->stream) == cudaSuccess) {
+      k_verify_div3<<<ctx->n_sm * 8, 256, 0, ctx->stream>>>(h.fixed_rad_sq, lo, n, ctx->d_kat);
+      if (cudaMemcpyAsync(&bad, ctx->d_kat, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+          cudaStreamSynchronize(ctx->stream) == cudaSuccess)
+        ok = bad == 0;
+    }
+    cudaGetLastError();
+  }
+  ctx->div3_cache.push_back({h.min_rad_sq, h.fixed_rad_sq, ok});
+  return ok;
+}
+
 int32_t rayn_b200_upload_scene(RaynContext* ctx, const RaynSceneDesc* s) {
   if (!ctx) return fail(nullptr, RAYN_ERR_INVALID_ARG, "ctx is NULL");
   int32_t rc = validate_scene(ctx, s);
@@ -421,6 +452,8 @@ int32_t rayn_b200_upload_scene(RaynContext* ctx, const RaynSceneDesc* s) {
   d.cam = s->camera;
   d.vol = s->volume;
   d.rc = s->consts;
+  for (int i = 0; i < d.n_hit; ++i)
+    ctx->sdf_var[i] = d.hit[i].kind == RAYN_HITABLE_SPHERE ? -1 : sdf_variant(d.hit[i], !(ctx->flags & RAYN_FLAG_NO_DIV3) && div3_verified(ctx, d.hit[i]));
   ctx->has_scene = true;
   return RAYN_OK;
 }
@@ -429,6 +462,11 @@ int32_t rayn_b200_get_stats(const RaynContext* ctx, RaynStats* out) {
   if (!ctx || !out) return RAYN_ERR_INVALID_ARG;
   *out = ctx->stats;
   return RAYN_OK;
+}
+
+int32_t rayn_b200_debug_sdf_variant(const RaynContext* ctx, int32_t hitable_index) {
+  if (!ctx || !ctx->has_scene || hitable_index < 0 || hitable_index >= ctx->scene.n_hit) return -2;
+  return ctx->sdf_var[hitable_index];
 }
 
 int32_t rayn_b200_debug_enable_queue_log(RaynContext* ctx, int32_t enable) {
@@ -660,7 +698,7 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
           }
           if (e < n_hit) {
             if (n_march++ > 0) CU(cudaMemsetAsync(ctx->d_work_ctr + WC_EXTEND, 0, sizeof(int), st));
-            const int v = sdf_variant(ctx->scene.hit[e]);
+            const int v = ctx->sdf_var[e];
             timed_begin(ctx, RAYN_K_EXTEND);
             DISPATCH_SDFV(v, (k_extend_march<V><<<ctx->n_sm * ctx->occ_ext[v], EXT_T, 0, st>>>(ctx->scene, pb, thr, e, ctx->d_batch_prefix, ctx->d_work_ctr + WC_EXTEND)));
             timed_end(ctx, RAYN_K_EXTEND);
@@ -691,7 +729,7 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
           const RaynHitable& h = ctx->scene.hit[sdf_idx[j]];
           const int mk = ctx->scene.mat[h.material].kind;
           if (!(mk == RAYN_MATERIAL_LAMBERTIAN || mk == RAYN_MATERIAL_DIELECTRIC || volume_on)) continue;
-          const int v = sdf_variant(h);
+          const int v = ctx->sdf_var[sdf_idx[j]];
           timed_begin(ctx, RAYN_K_NORMALS);
           DISPATCH_SDFV(v, (k_normals<V><<<g_shade, 128, 0, st>>>(ctx->scene, pb, thr, sdf_idx[j])));
           timed_end(ctx, RAYN_K_NORMALS);
@@ -701,7 +739,7 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
         timed_end(ctx, RAYN_K_SHADE_PRE);
         if (ctx->scene.n_lights > 0) {
           for (int j = 0; j < n_sdf; ++j) {
-            const int v = sdf_variant(ctx->scene.hit[sdf_idx[j]]);
+            const int v = ctx->sdf_var[sdf_idx[j]];
             timed_begin(ctx, RAYN_K_SHADOW);
             DISPATCH_SDFV(v, (k_shadow<V><<<ctx->n_sm * ctx->occ_shd[v], SHD_T, 0, st>>>(ctx->scene, pb, sdf_idx[j], j, ctx->d_work_ctr + WC_SHADOW + j)));
             timed_end(ctx, RAYN_K_SHADOW);
@@ -739,6 +777,7 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
       ctx->graph_stats = ctx->stats;
       ctx->graph_stats.reserved_ = 1;  // marks "replayed from a captured graph" for callers that look
       CU(cudaGraphLaunch(ctx->graph_exec, st));
+      ctx->stats.reserved_ = 1;  // this frame, too, ran as one graph launch
     }
     CU(cudaGetLastError());
   }
@@ -779,6 +818,8 @@ static int32_t render_finish(RaynContext* ctx) {
   ctx->stats.sdf_evals_normals = (int64_t)h[CNT_EVALS_NORMALS];
   ctx->stats.bulb_iters_extend = (int64_t)h[CNT_BULB_ITERS_EXTEND];
   ctx->stats.bulb_iters_shadow = (int64_t)h[CNT_BULB_ITERS_SHADOW];
+  ctx->stats.march_trips_extend = (int64_t)h[CNT_TRIPS_EXTEND];
+  ctx->stats.march_trips_shadow = (int64_t)h[CNT_TRIPS_SHADOW];
   {
     int64_t paths = 0;
     for (int idx : ctx->job_tiles) {
@@ -1165,9 +1206,10 @@ int32_t rayn_b200_kat_sdf_dist2(RaynContext* ctx, const RaynHitable* sdf, int32_
   KAT_PROLOGUE
   if (!sdf || !points3 || !out) return fail(ctx, RAYN_ERR_INVALID_ARG, "kat_sdf_dist2: NULL");
   if (sdf->kind == RAYN_HITABLE_SPHERE) return fail(ctx, RAYN_ERR_INVALID_ARG, "kat_sdf_dist2: not an SDF");
-  int v = variant < 0 ? sdf_variant(*sdf) : variant;
-  if (v >= SDFV_COUNT || (v == SDFV_BULB) != (sdf->kind == RAYN_HITABLE_MANDELBULB) ||
-      ((v == SDFV_BOX_12_FAST || v == SDFV_BOX_N_FAST) && !sdf_box_fast_ok(*sdf)) || (v == SDFV_BOX_12_FAST && sdf->iterations != 12))
+  int v = variant < 0 ? sdf_variant(*sdf, div3_verified(ctx, *sdf)) : variant;
+  const bool v_fast = v == SDFV_BOX_12_FAST || v == SDFV_BOX_N_FAST, v_div3 = v == SDFV_BOX_12_DIV3 || v == SDFV_BOX_N_DIV3;
+  if (v >= SDFV_COUNT || (v == SDFV_BULB) != (sdf->kind == RAYN_HITABLE_MANDELBULB) || ((v_fast || v_div3) && !sdf_box_fast_ok(*sdf)) ||
+      ((v == SDFV_BOX_12_FAST || v == SDFV_BOX_12_DIV3) && sdf->iterations != 12) || (v_div3 && !div3_verified(ctx, *sdf)))
     return fail(ctx, RAYN_ERR_INVALID_ARG, "kat_sdf_dist2: variant %d does not fit the hitable", v);
   float* dp = tmp.up(points3, 3 * n, &e);
   float* dout = tmp.up<float>(nullptr, n, &e);

@@ -72,7 +72,7 @@ struct PassBufs {
 };
 
 enum { CNT_EXTEND_RAYS = 0, CNT_SHADE_LANES = 1, CNT_SHADOW_RAYS = 2, CNT_EVALS_EXTEND = 3, CNT_EVALS_SHADOW = 4,
-       CNT_BULB_ITERS_EXTEND = 5, CNT_BULB_ITERS_SHADOW = 6, CNT_EVALS_NORMALS = 7, CNT_TOTAL = 8 };  // Mandelbulb iterations actually run (the count is data dependent)
+       CNT_BULB_ITERS_EXTEND = 5, CNT_BULB_ITERS_SHADOW = 6, CNT_EVALS_NORMALS = 7, CNT_TRIPS_EXTEND = 8, CNT_TRIPS_SHADOW = 9, CNT_TOTAL = 10 };  // Mandelbulb iterations actually run (the count is data dependent)
 
 // global work counters of the persistent kernels (RaynContext::d_work_ctr), zeroed by k_scan_live every depth
 enum { WC_EXTEND = 0, WC_SHADOW = 1 /* + SDF ordinal */, WC_SEG_COUNT = 1 + RAYN_MAX_HITABLES /* + SDF ordinal */, WC_TOTAL = 1 + 2 * RAYN_MAX_HITABLES };
@@ -344,99 +344,122 @@ __global__ void __launch_bounds__(EXT_T, RAYN_MARCH_OCC) k_extend_march(const __
   const unsigned lt = (1u << lane) - 1u;
   const float S = sc.rc.sdf_detail_scale;
   const float c0 = 0.00005f * S, c1 = 0.05f * S;
+  const bool c0_num = c0 == c0;  // max(c0, x) of the reference is NaN for a NaN c0: nothing ever "hits"
   const int max_marches = sc.rc.max_marches;
   const int n_batches = batch_prefix[pb.n_tiles];
-  bool have0 = false, have1 = false, first0 = false, first1 = false, exhausted = false;
-  float2 ox = splat2(0.0f), oy = ox, oz = ox, dx = ox, dy = ox, dz = ox, t = ox, closest = ox;
-  int g0 = 0, g1 = 0, steps0 = 0, steps1 = 0, evals = 0, bulb_iters = 0;
+  // slot state: g < 0 = empty; steps = -1 = the first evaluation (dist(origin), sdf.rs:60) is still to come.
+  // Component .x of every packed value belongs to slot 0, .y to slot 1.
+  pk2 ox = pk(0.0f, 0.0f), oy = ox, oz = ox, dx = ox, dy = ox, dz = ox;
+  float2 t = splat2(0.0f), closest = t;
+  int g0 = -1, g1 = -1, steps0 = -1, steps1 = -1, evals = 0, bulb_iters = 0, trips = 0;
   int cur_base = 0, cur_pos = 0, cur_end = 0;
+  bool exhausted = false;
   while (true) {
-    __syncwarp();
-    unsigned idle0 = __ballot_sync(0xffffffffu, !have0), idle1 = __ballot_sync(0xffffffffu, !have1);
-    while ((idle0 | idle1) && !(exhausted && cur_pos >= cur_end)) {
-      if (cur_pos >= cur_end) {
-        int b = 0;
-        if (lane == 0) b = atomicAdd(work_ctr, 1);
-        b = __shfl_sync(0xffffffffu, b, 0);
-        if (b >= n_batches) {
-          exhausted = true;
-          break;
+    if (!exhausted || cur_pos < cur_end) {
+      unsigned idle0 = __ballot_sync(0xffffffffu, g0 < 0), idle1 = __ballot_sync(0xffffffffu, g1 < 0);
+      while (idle0 | idle1) {
+        if (cur_pos >= cur_end) {
+          int b = 0;
+          if (lane == 0) b = atomicAdd(work_ctr, 1);
+          b = __shfl_sync(0xffffffffu, b, 0);
+          if (b >= n_batches) {
+            exhausted = true;
+            break;
+          }
+          int lo = 0, hi = pb.n_tiles;
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(batch_prefix + mid) <= b) lo = mid; else hi = mid;
+          }
+          cur_base = lo * pb.R;
+          cur_pos = (b - __ldg(batch_prefix + lo)) * EXT_BATCH;
+          cur_end = min(cur_pos + EXT_BATCH, pb.n_live[lo]);
         }
-        int lo = 0, hi = pb.n_tiles;
-        while (hi - lo > 1) {
-          const int mid = (lo + hi) >> 1;
-          if (__ldg(batch_prefix + mid) <= b) lo = mid; else hi = mid;
+        const int avail = cur_end - cur_pos;
+        const int n0 = __popc(idle0);
+        const int rank0 = __popc(idle0 & lt), rank1 = n0 + __popc(idle1 & lt);
+        if (g0 < 0 && rank0 < avail) {
+          g0 = cur_base + pb.q_live[cur_base + cur_pos + rank0];
+          const float4 o4 = pb.o_time[g0], d4 = pb.d_t[g0];
+          ox = pk_set_x(ox, o4.x), oy = pk_set_x(oy, o4.y), oz = pk_set_x(oz, o4.z);
+          dx = pk_set_x(dx, d4.x), dy = pk_set_x(dy, d4.y), dz = pk_set_x(dz, d4.z);
+          closest.x = d4.w, t.x = 0.0f, steps0 = -1;
         }
-        cur_base = lo * pb.R;
-        cur_pos = (b - __ldg(batch_prefix + lo)) * EXT_BATCH;
-        cur_end = min(cur_pos + EXT_BATCH, pb.n_live[lo]);
+        if (g1 < 0 && rank1 < avail) {
+          g1 = cur_base + pb.q_live[cur_base + cur_pos + rank1];
+          const float4 o4 = pb.o_time[g1], d4 = pb.d_t[g1];
+          ox = pk_set_y(ox, o4.x), oy = pk_set_y(oy, o4.y), oz = pk_set_y(oz, o4.z);
+          dx = pk_set_y(dx, d4.x), dy = pk_set_y(dy, d4.y), dz = pk_set_y(dz, d4.z);
+          closest.y = d4.w, t.y = 0.0f, steps1 = -1;
+        }
+        cur_pos += min(avail, n0 + __popc(idle1));
+        idle0 = __ballot_sync(0xffffffffu, g0 < 0), idle1 = __ballot_sync(0xffffffffu, g1 < 0);
       }
-      const int avail = cur_end - cur_pos;
-      const int n0 = __popc(idle0);
-      const int rank0 = __popc(idle0 & lt), rank1 = n0 + __popc(idle1 & lt);
-      if (!have0 && rank0 < avail) {
-        g0 = cur_base + pb.q_live[cur_base + cur_pos + rank0];
-        const float4 o4 = pb.o_time[g0], d4 = pb.d_t[g0];
-        ox.x = o4.x, oy.x = o4.y, oz.x = o4.z, dx.x = d4.x, dy.x = d4.y, dz.x = d4.z, closest.x = d4.w;
-        first0 = have0 = true;
-      }
-      if (!have1 && rank1 < avail) {
-        g1 = cur_base + pb.q_live[cur_base + cur_pos + rank1];
-        const float4 o4 = pb.o_time[g1], d4 = pb.d_t[g1];
-        ox.y = o4.x, oy.y = o4.y, oz.y = o4.z, dx.y = d4.x, dy.y = d4.y, dz.y = d4.z, closest.y = d4.w;
-        first1 = have1 = true;
-      }
-      cur_pos += min(avail, n0 + __popc(idle1));
-      idle0 = __ballot_sync(0xffffffffu, !have0), idle1 = __ballot_sync(0xffffffffu, !have1);
     }
-    if (!__any_sync(0xffffffffu, have0 || have1)) break;
+    // while work remains every slot is busy here; slots stay empty only in the tail of the kernel, where they are parked on a
+    // far point (cheapest for every estimator: the Mandelbulb leaves its loop at once and counts no iteration)
+    if (exhausted) {
+      if (!__any_sync(0xffffffffu, g0 >= 0 || g1 >= 0)) break;
+      if (g0 < 0) ox = pk_set_x(ox, 100.0f), oy = pk_set_x(oy, 0.0f), oz = pk_set_x(oz, 0.0f), steps0 = -1;
+      if (g1 < 0) ox = pk_set_y(ox, 100.0f), oy = pk_set_y(oy, 0.0f), oz = pk_set_y(oz, 0.0f), steps1 = -1;
+    }
     // evaluation point of each slot: the origin for the first evaluation (sdf.rs:60), ray.point_at(t) afterwards
-    // (ray.rs:22-24: dir.mul_add(t, origin)); an empty slot evaluates a far point (cheapest for every estimator)
-    float2 px = muladd2(dx, t, ox, k.one), py = muladd2(dy, t, oy, k.one), pz = muladd2(dz, t, oz, k.one);
-    if (first0) px.x = ox.x, py.x = oy.x, pz.x = oz.x;
-    if (first1) px.y = ox.y, py.y = oy.y, pz.y = oz.y;
-    if (!have0) px.x = 100.0f, py.x = 0.0f, pz.x = 0.0f;
-    if (!have1) px.y = 100.0f, py.y = 0.0f, pz.y = 0.0f;
+    // (ray.rs:22-24: dir.mul_add(t, origin))
+    const bool first0 = steps0 < 0, first1 = steps1 < 0;
+    const float2 o_x = un(ox), o_y = un(oy), o_z = un(oz);
+    float2 px = muladd2(un(dx), t, o_x, k.one), py = muladd2(un(dy), t, o_y, k.one), pz = muladd2(un(dz), t, o_z, k.one);
+    if (first0) px.x = o_x.x, py.x = o_y.x, pz.x = o_z.x;
+    if (first1) px.y = o_x.y, py.y = o_y.y, pz.y = o_z.y;
     const float2 dd = sdf_dist2<V>(k, px, py, pz, bulb_iters);
-    // per-slot march step, branch-free over `first` so that all busy lanes of the warp run ONE code path:
-    //   first evaluation (sdf.rs:60-61): t = dist(origin); a NaN start ends the march (the caller's t < closest is false);
-    //   later (sdf.rs:65-80): stop on hit or t > t_max, else t += dist; a NaN t can never satisfy hit/gt again and the
-    //   reference marches it to exhaustion and returns NaN - ending at once returns the same NaN.
-    evals += (have0 ? 1 : 0) + (have1 ? 1 : 0);
+    ++trips;
+    // per-slot march step, branch-free up to the (rare) end of a march:
+    //   first evaluation (sdf.rs:60-61): t = dist(origin), no hit test; a NaN start ends the march (the caller's t < closest is false);
+    //   later (sdf.rs:65-80): stop on |dist| < max(0.00005 S, 0.05 S threshold(t)) or t > t_max, else t += dist; a NaN t can never
+    //   satisfy hit/gt again, the reference marches it to exhaustion and returns NaN - ending at once returns the same NaN.
+    //   max(c0, x) = (c0 < x ? x : c0): for a non-NaN c0, |d| < max(c0, x) <=> |d| < c0 || |d| < x  (x NaN: both sides |d| < c0).
+    const float2 th = mul2(splat2(c1), thr.is_const ? splat2(thr.scale) : mul2(splat2(thr.scale), t));
+    const float2 tsum = add2(t, dd);
+    // (bitwise & | on the predicates: no short-circuit branches in the per-trip path)
+    bool done0, done1, stop0, stop1;
     {
-      const bool stop = !first0 && ((dm::abs(dd.x) < dm::max(c0, c1 * thr.at(t.x))) || t.x > closest.x);
-      const float tn = first0 ? dd.x : t.x + dd.x;
-      const int sn = first0 ? 0 : steps0 + 1;
-      if (have0) {
-        if (!stop) t.x = tn, steps0 = sn;
-        first0 = false;
-        if (stop || (tn != tn) || sn >= max_marches) {
-          if (t.x < closest.x) {  // hitable.rs:190-193
-            pb.d_t[g0].w = t.x;
-            pb.q_key[g0] = hk;
-          }
-          have0 = false;
-        }
-      }
+      const float ad = dm::abs(dd.x);
+      stop0 = !first0 & ((c0_num & ((ad < c0) | (ad < th.x))) | (t.x > closest.x));
+      const float tn = first0 ? dd.x : tsum.x;
+      const int sn = steps0 + 1;
+      t.x = stop0 ? t.x : tn;
+      steps0 = stop0 ? steps0 : sn;
+      done0 = stop0 | (tn != tn) | (sn >= max_marches);
     }
     {
-      const bool stop = !first1 && ((dm::abs(dd.y) < dm::max(c0, c1 * thr.at(t.y))) || t.y > closest.y);
-      const float tn = first1 ? dd.y : t.y + dd.y;
-      const int sn = first1 ? 0 : steps1 + 1;
-      if (have1) {
-        if (!stop) t.y = tn, steps1 = sn;
-        first1 = false;
-        if (stop || (tn != tn) || sn >= max_marches) {
-          if (t.y < closest.y) {
-            pb.d_t[g1].w = t.y;
-            pb.q_key[g1] = hk;
-          }
-          have1 = false;
+      const float ad = dm::abs(dd.y);
+      stop1 = !first1 & ((c0_num & ((ad < c0) | (ad < th.y))) | (t.y > closest.y));
+      const float tn = first1 ? dd.y : tsum.y;
+      const int sn = steps1 + 1;
+      t.y = stop1 ? t.y : tn;
+      steps1 = stop1 ? steps1 : sn;
+      done1 = stop1 | (tn != tn) | (sn >= max_marches);
+    }
+    if (done0 | done1) {
+      if (done0 & (g0 >= 0)) {
+        if (t.x < closest.x) {  // hitable.rs:190-193
+          pb.d_t[g0].w = t.x;
+          pb.q_key[g0] = hk;
         }
+        evals += steps0 + (stop0 ? 2 : 1);  // distance evaluations this march took
+        g0 = -1;
+      }
+      if (done1 & (g1 >= 0)) {
+        if (t.y < closest.y) {
+          pb.d_t[g1].w = t.y;
+          pb.q_key[g1] = hk;
+        }
+        evals += steps1 + (stop1 ? 2 : 1);
+        g1 = -1;
       }
     }
   }
   warp_add(pb.counters + CNT_EVALS_EXTEND, evals);
+  if (lane == 0) atomicAdd(pb.counters + CNT_TRIPS_EXTEND, (unsigned long long)trips);
   if (V == SDFV_BULB) warp_add(pb.counters + CNT_BULB_ITERS_EXTEND, bulb_iters);
 }
 
@@ -523,13 +546,19 @@ struct SlotCtx {  // what pre and post both derive for a shading slot
   unsigned w0, w1, w2;  // light indices of the packet, one byte per packet lane, per round
   int set1, set2;
 };
+// Memory-level parallelism matters here (r02a profile: both shade kernels sit on long-scoreboard stalls at ~23 % issue
+// utilisation): everything a slot needs hangs off ONE dependent load, its path id, so that the hit object (q_key is indexed
+// by path), the pixel's scramble value and the sampler-table entries are all in flight together - the former search of the
+// tile's bin_start row was a chain of up to n_hit dependent loads.
 RT_D SlotCtx slot_ctx(const DevScene& sc, const DevFrame& fr, const PassBufs& pb, int ts, int s, int nslots, int depth, int lane) {
   SlotCtx c;
   const int* __restrict__ qs = pb.q_shade + (size_t)ts * pb.QS;
   c.id = s < nslots ? qs[s] : -1;
   c.sample = 0;
+  c.obj = 0;
   c.scramble = 0.0f;  // padded lanes are Ray::new_invalid: sample 0, scramble 0 (ray.rs:54-66)
   if (c.id >= 0) {
+    c.obj = pb.q_key[(size_t)ts * pb.R + c.id];  // the bin this slot sits in (k_bin partitions by this key)
     const TileGeom tg = tile_geom(fr, pb.tile_ids[ts]);
     const int pl = c.id / fr.spp;
     c.sample = c.id - pl * fr.spp;
@@ -541,10 +570,12 @@ RT_D SlotCtx slot_ctx(const DevScene& sc, const DevFrame& fr, const PassBufs& pb
   c.set2 = 2 + depth * n2h;
   const int nl = sc.n_lights;
   unsigned pack = 0;
-  if (nl > 0)
-    pack = (unsigned)light_index(samp1(fr, c.sample, c.scramble, c.set1 + 0), nl) |
-           ((unsigned)light_index(samp1(fr, c.sample, c.scramble, c.set1 + 1), nl) << 8) |
-           ((unsigned)light_index(samp1(fr, c.sample, c.scramble, c.set1 + 2), nl) << 16);
+  if (nl > 0) {
+    const float u0 = __ldg(fr.s1 + c.sample + (size_t)fr.spp * (c.set1 + 0)), u1 = __ldg(fr.s1 + c.sample + (size_t)fr.spp * (c.set1 + 1)),
+                u2 = __ldg(fr.s1 + c.sample + (size_t)fr.spp * (c.set1 + 2));  // three independent loads, then samp1's fract(x + scramble)
+    pack = (unsigned)light_index(dm::fract(u0 + c.scramble), nl) | ((unsigned)light_index(dm::fract(u1 + c.scramble), nl) << 8) |
+           ((unsigned)light_index(dm::fract(u2 + c.scramble), nl) << 16);
+  }
   c.w0 = c.w1 = c.w2 = 0;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
@@ -552,11 +583,6 @@ RT_D SlotCtx slot_ctx(const DevScene& sc, const DevFrame& fr, const PassBufs& pb
     c.w0 |= (pk & 0xffu) << (8 * k);
     c.w1 |= ((pk >> 8) & 0xffu) << (8 * k);
     c.w2 |= ((pk >> 16) & 0xffu) << (8 * k);
-  }
-  c.obj = 0;
-  if (c.id >= 0) {
-    const int* __restrict__ bs = pb.bin_start + ts * (RAYN_MAX_HITABLES + 1);
-    while (c.obj + 1 < sc.n_hit && s >= bs[c.obj + 1]) ++c.obj;
   }
   return c;
 }
@@ -572,15 +598,14 @@ __global__ void __launch_bounds__(128, 8) k_shade_pre(const __grid_constant__ De
   warp_add(pb.counters + CNT_SHADE_LANES, valid ? 1 : 0);
   int shadows = 0;
   const size_t g = (size_t)ts * pb.R + (valid ? cx.id : 0);
-  float4 o4 = make_float4(0, 0, 0, 0);
-  if (valid) o4 = pb.o_time[g];
+  float4 o4 = make_float4(0, 0, 0, 0), d4 = o4, r4 = o4, t4 = o4;
+  if (valid) o4 = pb.o_time[g], d4 = pb.d_t[g], r4 = pb.rad[g], t4 = pb.thr[g];  // all in flight before the shuffle below waits for o4
   // time of lane 0 of this shading packet (bins pad at the tail, so lane 0 of a non-empty packet is valid): what a
   // closure-backed Sphere centre is evaluated at in occluded() / get_shading_info() (sphere.rs:29,80; animation.rs:62-67)
   const float time0 = __shfl_sync(0xffffffffu, o4.w, (threadIdx.x & 31) & ~3);
   if (valid) {
     const RaynHitable& h = sc.hit[cx.obj];
     const RaynMaterial& mat = sc.mat[h.material];
-    const float4 d4 = pb.d_t[g], r4 = pb.rad[g], t4 = pb.thr[g];
     ShadingPoint sp;
     sp.o = mk3(o4.x, o4.y, o4.z);
     sp.d = mk3(d4.x, d4.y, d4.z);
@@ -680,77 +705,99 @@ __global__ void __launch_bounds__(SHD_T, RAYN_MARCH_OCC) k_shadow(const __grid_c
   const float4* __restrict__ seg_b = pb.seg_b + (size_t)j * pb.seg_cap;
   const float S = sc.rc.sdf_detail_scale;
   const float oc0 = 0.0001f * S, oc1 = 0.00001f * S;
+  const bool oc0_num = oc0 == oc0;  // see k_extend_march
   const int max_vis = sc.rc.max_vis_marches;
-  bool have0 = false, have1 = false, first0 = false, first1 = false, exhausted = false;
-  float2 sx = splat2(0.0f), sy = sx, sz = sx, dx = sx, dy = sx, dz = sx, t = sx, max_dist = sx;
-  int own0 = 0, own1 = 0, steps0 = 0, steps1 = 0, evals = 0, bulb_iters = 0;
+  // slot state (see k_extend_march): own < 0 = empty, steps = -1 = dist(start) (sdf.rs:30) still to come
+  pk2 sx = pk(0.0f, 0.0f), sy = sx, sz = sx, dx = sx, dy = sx, dz = sx;
+  float2 t = splat2(0.0f), max_dist = t;
+  int own0 = -1, own1 = -1, steps0 = -1, steps1 = -1, evals = 0, bulb_iters = 0, trips = 0;
   int cur_pos = 0, cur_end = 0;
+  bool exhausted = false;
   while (true) {
-    __syncwarp();
-    unsigned idle0 = __ballot_sync(0xffffffffu, !have0), idle1 = __ballot_sync(0xffffffffu, !have1);
-    while ((idle0 | idle1) && !(exhausted && cur_pos >= cur_end)) {
-      if (cur_pos >= cur_end) {
-        int b = 0;
-        if (lane == 0) b = atomicAdd(work_ctr, SHD_BATCH);
-        b = __shfl_sync(0xffffffffu, b, 0);
-        if (b >= n_seg) {
-          exhausted = true;
-          break;
+    if (!exhausted || cur_pos < cur_end) {
+      unsigned idle0 = __ballot_sync(0xffffffffu, own0 < 0), idle1 = __ballot_sync(0xffffffffu, own1 < 0);
+      while (idle0 | idle1) {
+        if (cur_pos >= cur_end) {
+          int b = 0;
+          if (lane == 0) b = atomicAdd(work_ctr, SHD_BATCH);
+          b = __shfl_sync(0xffffffffu, b, 0);
+          if (b >= n_seg) {
+            exhausted = true;
+            break;
+          }
+          cur_pos = b;
+          cur_end = min(b + SHD_BATCH, n_seg);
         }
-        cur_pos = b;
-        cur_end = min(b + SHD_BATCH, n_seg);
+        const int avail = cur_end - cur_pos;
+        const int n0 = __popc(idle0);
+        const int rank0 = __popc(idle0 & lt), rank1 = n0 + __popc(idle1 & lt);
+        if (own0 < 0 && rank0 < avail) {
+          const float4 a = seg_a[cur_pos + rank0], b4 = seg_b[cur_pos + rank0];
+          sx = pk_set_x(sx, a.x), sy = pk_set_x(sy, a.y), sz = pk_set_x(sz, a.z);
+          dx = pk_set_x(dx, b4.x), dy = pk_set_x(dy, b4.y), dz = pk_set_x(dz, b4.z);
+          max_dist.x = a.w, t.x = 0.0f, steps0 = -1;
+          own0 = __float_as_int(b4.w);
+        }
+        if (own1 < 0 && rank1 < avail) {
+          const float4 a = seg_a[cur_pos + rank1], b4 = seg_b[cur_pos + rank1];
+          sx = pk_set_y(sx, a.x), sy = pk_set_y(sy, a.y), sz = pk_set_y(sz, a.z);
+          dx = pk_set_y(dx, b4.x), dy = pk_set_y(dy, b4.y), dz = pk_set_y(dz, b4.z);
+          max_dist.y = a.w, t.y = 0.0f, steps1 = -1;
+          own1 = __float_as_int(b4.w);
+        }
+        cur_pos += min(avail, n0 + __popc(idle1));
+        idle0 = __ballot_sync(0xffffffffu, own0 < 0), idle1 = __ballot_sync(0xffffffffu, own1 < 0);
       }
-      const int avail = cur_end - cur_pos;
-      const int n0 = __popc(idle0);
-      const int rank0 = __popc(idle0 & lt), rank1 = n0 + __popc(idle1 & lt);
-      if (!have0 && rank0 < avail) {
-        const float4 a = seg_a[cur_pos + rank0], b4 = seg_b[cur_pos + rank0];
-        sx.x = a.x, sy.x = a.y, sz.x = a.z, max_dist.x = a.w, dx.x = b4.x, dy.x = b4.y, dz.x = b4.z;
-        own0 = __float_as_int(b4.w);
-        first0 = have0 = true;
-      }
-      if (!have1 && rank1 < avail) {
-        const float4 a = seg_a[cur_pos + rank1], b4 = seg_b[cur_pos + rank1];
-        sx.y = a.x, sy.y = a.y, sz.y = a.z, max_dist.y = a.w, dx.y = b4.x, dy.y = b4.y, dz.y = b4.z;
-        own1 = __float_as_int(b4.w);
-        first1 = have1 = true;
-      }
-      cur_pos += min(avail, n0 + __popc(idle1));
-      idle0 = __ballot_sync(0xffffffffu, !have0), idle1 = __ballot_sync(0xffffffffu, !have1);
     }
-    if (!__any_sync(0xffffffffu, have0 || have1)) break;
-    float2 px = muladd2(dx, t, sx, k.one), py = muladd2(dy, t, sy, k.one), pz = muladd2(dz, t, sz, k.one);  // dir.mul_add(t, start), sdf.rs:45
-    if (first0) px.x = sx.x, py.x = sy.x, pz.x = sz.x;                                 // dist(start), sdf.rs:30
-    if (first1) px.y = sx.y, py.y = sy.y, pz.y = sz.y;
-    if (!have0) px.x = 100.0f, py.x = 0.0f, pz.x = 0.0f;
-    if (!have1) px.y = 100.0f, py.y = 0.0f, pz.y = 0.0f;
+    if (exhausted) {  // tail of the kernel: empty slots are parked on a far point (see k_extend_march)
+      if (!__any_sync(0xffffffffu, own0 >= 0 || own1 >= 0)) break;
+      if (own0 < 0) sx = pk_set_x(sx, 100.0f), sy = pk_set_x(sy, 0.0f), sz = pk_set_x(sz, 0.0f), steps0 = -1;
+      if (own1 < 0) sx = pk_set_y(sx, 100.0f), sy = pk_set_y(sy, 0.0f), sz = pk_set_y(sz, 0.0f), steps1 = -1;
+    }
+    const bool first0 = steps0 < 0, first1 = steps1 < 0;
+    const float2 s_x = un(sx), s_y = un(sy), s_z = un(sz);
+    float2 px = muladd2(un(dx), t, s_x, k.one), py = muladd2(un(dy), t, s_y, k.one), pz = muladd2(un(dz), t, s_z, k.one);  // dir.mul_add(t, start), sdf.rs:45
+    if (first0) px.x = s_x.x, py.x = s_y.x, pz.x = s_z.x;                                                                  // dist(start), sdf.rs:30
+    if (first1) px.y = s_x.y, py.y = s_y.y, pz.y = s_z.y;
     const float2 dd = sdf_dist2<V>(k, px, py, pz, bulb_iters);
-    // per-slot step of TracedSDF::occluded, branch-free over `first` (see k_extend_march):
+    ++trips;
+    // per-slot step of TracedSDF::occluded, branch-free up to the end of a march (see k_extend_march):
     //   first (sdf.rs:30-36): t = dist(start);   later (:40-55): occluded when |dist| < max(1e-4 S, 1e-5 S t), else t += dist;
     //   the march ends unoccluded when t is NaN, exceeds max_dist, or after MAX_VIS_MARCHES steps.
-    evals += (have0 ? 1 : 0) + (have1 ? 1 : 0);
+    const float2 th = mul2(splat2(oc1), t);
+    const float2 tsum = add2(t, dd);
+    bool done0, done1, occ0, occ1;
     {
-      const bool occ = !first0 && (dm::abs(dd.x) < dm::max(oc0, oc1 * t.x));
-      const float tn = first0 ? dd.x : t.x + dd.x;
-      const int sn = first0 ? 0 : steps0 + 1;
-      if (have0) {
-        if (occ) atomicAnd(pb.vis + ((unsigned)own0 >> 4), ~(1u << (own0 & 15)));
-        t.x = tn, steps0 = sn, first0 = false;
-        if (occ || (tn != tn) || sn >= max_vis || tn > max_dist.x) have0 = false;
-      }
+      const float ad = dm::abs(dd.x);
+      occ0 = !first0 & oc0_num & ((ad < oc0) | (ad < th.x));
+      const float tn = first0 ? dd.x : tsum.x;
+      t.x = tn;
+      steps0 = steps0 + 1;
+      done0 = occ0 | (tn != tn) | (steps0 >= max_vis) | (tn > max_dist.x);
     }
     {
-      const bool occ = !first1 && (dm::abs(dd.y) < dm::max(oc0, oc1 * t.y));
-      const float tn = first1 ? dd.y : t.y + dd.y;
-      const int sn = first1 ? 0 : steps1 + 1;
-      if (have1) {
-        if (occ) atomicAnd(pb.vis + ((unsigned)own1 >> 4), ~(1u << (own1 & 15)));
-        t.y = tn, steps1 = sn, first1 = false;
-        if (occ || (tn != tn) || sn >= max_vis || tn > max_dist.y) have1 = false;
+      const float ad = dm::abs(dd.y);
+      occ1 = !first1 & oc0_num & ((ad < oc0) | (ad < th.y));
+      const float tn = first1 ? dd.y : tsum.y;
+      t.y = tn;
+      steps1 = steps1 + 1;
+      done1 = occ1 | (tn != tn) | (steps1 >= max_vis) | (tn > max_dist.y);
+    }
+    if (done0 | done1) {
+      if (done0 & (own0 >= 0)) {
+        if (occ0) atomicAnd(pb.vis + ((unsigned)own0 >> 4), ~(1u << (own0 & 15)));
+        evals += steps0 + 1;  // distance evaluations this march took
+        own0 = -1;
+      }
+      if (done1 & (own1 >= 0)) {
+        if (occ1) atomicAnd(pb.vis + ((unsigned)own1 >> 4), ~(1u << (own1 & 15)));
+        evals += steps1 + 1;
+        own1 = -1;
       }
     }
   }
   warp_add(pb.counters + CNT_EVALS_SHADOW, evals);
+  if (lane == 0) atomicAdd(pb.counters + CNT_TRIPS_SHADOW, (unsigned long long)trips);
   if (V == SDFV_BULB) warp_add(pb.counters + CNT_BULB_ITERS_SHADOW, bulb_iters);
 }
 
@@ -1174,6 +1221,18 @@ __global__ void k_kat_fastdiv(float num, unsigned first_bits, long long n, unsig
     const float ref = num / x;
     bad = (__float_as_uint(q.x) != __float_as_uint(ref)) + (__float_as_uint(q.y) != __float_as_uint(ref)) +
           (__float_as_uint(fastdiv1(num, x)) != __float_as_uint(ref));
+  }
+  warp_add(mismatches, bad);
+}
+// rt_sdf2.cuh::fastdiv2_3 against IEEE division over n consecutive divisors (grid-stride): the check behind the DIV3 variants
+__global__ void __launch_bounds__(256) k_verify_div3(float num, unsigned first_bits, unsigned long long n, unsigned long long* mismatches) {
+  int bad = 0;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+    const float x = __uint_as_float(first_bits + (unsigned)i);
+    const float2 q = fastdiv2_3(num, f2(x, x));
+    const float ref = num / x;
+    bad += (__float_as_uint(q.x) != __float_as_uint(ref)) | (__float_as_uint(q.y) != __float_as_uint(ref)) |
+           (__float_as_uint(fastdiv1_3(num, x)) != __float_as_uint(ref));
   }
   warp_add(mismatches, bad);
 }

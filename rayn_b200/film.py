@@ -210,6 +210,10 @@ class Renderer:
                                              _fptr(pdf), _fptr(fe)), self._ctx)
         return wi, f, pdf, fe
 
+    def sdf_variant(self, hitable_index):
+        """march-kernel specialisation upload_scene selected for a hitable (include/rayn_b200.h: rayn_b200_debug_sdf_variant)"""
+        return int(self._lib.rayn_b200_debug_sdf_variant(self._ctx, hitable_index))
+
     def enable_queue_log(self, on=True):
         L.check(self._lib.rayn_b200_debug_enable_queue_log(self._ctx, 1 if on else 0), self._ctx)
 

@@ -159,7 +159,7 @@ def test_small_frames_replay_a_cuda_graph_and_stay_bit_exact(oracle):
             r.render(fd, planes)
             st = r.stats()
             launches.append(st.launches)
-            assert st.reserved_ == 1, "frame was not served by the captured graph"
+            assert st.reserved_ == 1, f"frame {i} was not served by the captured graph"
             got = store.cpu().numpy()
             for ch, (a, b) in zip(CH, ((0, 3), (3, 4), (4, 7), (7, 10))):
                 assert_bit_equal(got[a * npx:b * npx], o[ch], f"graph frame {i} {ch}")

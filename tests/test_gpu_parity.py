@@ -60,7 +60,7 @@ def test_sdf_dist_bit_equal(renderer, oracle, kind):
     assert_bit_equal(renderer.kat_sdf_dist(h, p), oracle.kat_sdf_dist(h, p), f"{kind} dist")
 
 
-@pytest.mark.parametrize("kind,variants", [("mandelbox", (-1, 0, 1, 2)), ("mandelbulb", (-1, 3))])
+@pytest.mark.parametrize("kind,variants", [("mandelbox", (-1, 0, 1, 2, 4, 5)), ("mandelbulb", (-1, 3))])
 def test_packed_two_point_estimator_bit_equal(renderer, oracle, kind, variants):
     """rt_sdf2.cuh: the f32x2 (FFMA2/FMUL2/FADD2) two-point estimators the march kernels run, every specialisation,
     against the oracle's 4-lane SSE estimator; odd point count exercises the half-filled last pair."""
@@ -83,8 +83,28 @@ def test_packed_two_point_estimator_bit_equal(renderer, oracle, kind, variants):
             h2 = copy.copy(h)
             h2.iterations, h2.box_l, h2.min_rad_sq, h2.fixed_rad_sq, h2.scale = iters, l, mn, fx, sc
             ref2 = oracle.kat_sdf_dist(h2, p)
-            for v in (-1, 0, 2):
+            for v in (-1, 0, 2) + ((5,) if mn <= fx else ()):  # 5 = three-operation division, needs a non-empty divisor interval
                 assert_bit_equal(renderer.kat_sdf_dist2(h2, p, v), ref2, f"mandelbox {iters, l, mn, fx, sc} variant {v}")
+
+
+def test_three_operation_division_is_selected_only_after_its_exhaustive_check(oracle):
+    """upload_scene divides by every float of [min_rad_sq, fixed_rad_sq] on the device and selects the three-operation
+    sphere-fold division (variants 4 / 5) only if all quotients equal IEEE division; RAYN_FLAG_NO_DIV3 keeps the
+    five-operation form.  Both render the oracle's film."""
+    c, inp = small_config(3, (48, 48), 2, 4)
+    o, _ = oracle.render(c["world"], c["camera"], inp, (16, 16), c["integrator"], TR)
+    sdf_index = [i for i, h in enumerate(c["world"].hitables.items) if hasattr(h, "sdf")][0]
+    for flags, want in ((0, (4,)), (L.FLAG_NO_DIV3, (1,))):
+        r = Renderer(0, flags=flags)
+        try:
+            r.upload_scene(c["world"], c["camera"])
+            assert r.sdf_variant(sdf_index) in want, (flags, r.sdf_variant(sdf_index))
+            assert r.sdf_variant(0) == -1 and r.sdf_variant(99) == -2
+            g = r.render_host(inp, (16, 16), c["integrator"], TR)
+        finally:
+            r.close()
+        for ch in CH:
+            assert_bit_equal(g[ch], o[ch], f"flags {flags} {ch}")
 
 
 def test_fastdiv_equals_ieee_division(renderer):
