@@ -452,6 +452,19 @@ int32_t rayn_b200_upload_scene(RaynContext* ctx, const RaynSceneDesc* s) {
   d.cam = s->camera;
   d.vol = s->volume;
   d.rc = s->consts;
+  for (int i = 0; i < d.n_hit; ++i) {  // compact sphere / SDF lists in insertion order (DevScene)
+    const RaynHitable& h = d.hit[i];
+    if (h.kind == RAYN_HITABLE_SPHERE) {
+      d.sph_idx[d.n_sph] = i;
+      d.hit_ord[i] = d.n_sph;
+      d.sph[d.n_sph] = make_float4(h.center[0], h.center[1], h.center[2], h.radius);
+      d.sph_moving |= (h.center_velocity[0] != 0.0f || h.center_velocity[1] != 0.0f || h.center_velocity[2] != 0.0f) ? 1 : 0;
+      ++d.n_sph;
+    } else {
+      d.hit_ord[i] = d.n_sdf;
+      d.sdf_idx[d.n_sdf++] = i;
+    }
+  }
   for (int i = 0; i < d.n_hit; ++i)
     ctx->sdf_var[i] = d.hit[i].kind == RAYN_HITABLE_SPHERE ? -1 : sdf_variant(d.hit[i], !(ctx->flags & RAYN_FLAG_NO_DIV3) && div3_verified(ctx, d.hit[i]));
   ctx->has_scene = true;
@@ -604,6 +617,13 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
     fold_pre = 0;
     while (fold_pre < n_hit && ctx->scene.hit[fold_pre].kind == RAYN_HITABLE_SPHERE) ++fold_pre;
   }
+  // Scenes of the shape [spheres] Mandelbox [spheres] (setup.rs) fold ALL analytic spheres into the producing kernel and march
+  // the SDF last, against the nearest sphere: one gather of every live ray per depth less (k_extend_spheres was 2 % of a
+  // config-3 frame) and shorter marches for rays that end on an emitter.  The result is the reference's fold bit for bit
+  // (proof in rt_kernels.cuh at k_extend_march: it needs a distance estimator that is never negative, i.e. the Mandelbox -
+  // sqrt(m) / |dr| - so that a march's t never decreases, and the first-index-wins tie rule, which the kernel applies).
+  const bool fold_all = fold_pre >= 0 && n_sdf == 1 && ctx->scene.hit[sdf_idx[0]].kind == RAYN_HITABLE_MANDELBOX && !(ctx->flags & RAYN_FLAG_NO_FOLD_ALL);
+  const int n_fold = fold_all ? ctx->scene.n_sph : fold_pre;  // leading spheres are the first fold_pre entries of the compact sphere list
   const bool volume_on = ctx->scene.vol.has_scattering != 0 && ctx->scene.n_lights > 0;
   const int ns = volume_on ? 4 * (1 + vm) : 4;               // light samples per path per depth
   const int seg_per_path = simple ? 0 : ns * n_sdf;          // worst case shadow segments per path per depth, all SDF queues
@@ -648,7 +668,7 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
     key = fnv1a(key, &kpb, sizeof kpb);
     float* planes4[4] = {p_color, p_alpha, p_bg, p_normal};
     key = fnv1a(key, planes4, sizeof planes4);
-    const int misc[6] = {np, wpc, mb, fold_pre, simple ? 1 : 0, motion ? 1 : 0};
+    const int misc[6] = {np, wpc, mb, n_fold, simple ? 1 : 0, motion ? 1 : 0};
     key = fnv1a(key, misc, sizeof misc);
     key = fnv1a(key, my_tiles.data(), my_tiles.size() * sizeof(int));
     if (ctx->graph_exec && ctx->graph_key == key) {
@@ -670,7 +690,7 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
     ctx->stats.passes++;
     const dim3 g_paths((R + 255) / 256, nt), g_shade((QS + 127) / 128, nt);
     timed_begin(ctx, RAYN_K_RAYGEN);
-    k_raygen<<<g_paths, 256, 0, st>>>(ctx->scene, fr, pb, fold_pre);
+    k_raygen<<<g_paths, 256, 0, st>>>(ctx->scene, fr, pb, n_fold);
     timed_end(ctx, RAYN_K_RAYGEN);
     for (int depth = 0; depth <= mb; ++depth) {
       const Thr thr = make_thr(ctx->scene.cam, depth);
@@ -690,7 +710,7 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
         while (k < n_hit || first_kernel) {
           int e = k;
           while (e < n_hit && ctx->scene.hit[e].kind == RAYN_HITABLE_SPHERE) ++e;
-          if (e > k || first_kernel) {
+          if ((e > k || first_kernel) && !fold_all) {
             timed_begin(ctx, RAYN_K_EXTEND_SPHERES);
             k_extend_spheres<<<g_paths, 256, 0, st>>>(ctx->scene, pb, k, e, first_kernel, motion ? 1 : 0);
             timed_end(ctx, RAYN_K_EXTEND_SPHERES);
@@ -700,7 +720,7 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
             if (n_march++ > 0) CU(cudaMemsetAsync(ctx->d_work_ctr + WC_EXTEND, 0, sizeof(int), st));
             const int v = ctx->sdf_var[e];
             timed_begin(ctx, RAYN_K_EXTEND);
-            DISPATCH_SDFV(v, (k_extend_march<V><<<ctx->n_sm * ctx->occ_ext[v], EXT_T, 0, st>>>(ctx->scene, pb, thr, e, ctx->d_batch_prefix, ctx->d_work_ctr + WC_EXTEND)));
+            DISPATCH_SDFV(v, (k_extend_march<V><<<ctx->n_sm * ctx->occ_ext[v], EXT_T, 0, st>>>(ctx->scene, pb, thr, e, fold_all ? 1 : 0, ctx->d_batch_prefix, ctx->d_work_ctr + WC_EXTEND)));
             timed_end(ctx, RAYN_K_EXTEND);
             ++e;
           }
@@ -746,7 +766,7 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
           }
         }
         timed_begin(ctx, RAYN_K_SHADE_POST);
-        k_shade_post<<<g_shade, 128, 0, st>>>(ctx->scene, fr, pb, depth, fold_pre);
+        k_shade_post<<<g_shade, 128, 0, st>>>(ctx->scene, fr, pb, depth, n_fold);
         timed_end(ctx, RAYN_K_SHADE_POST);
       } else {
 #ifdef RAYN_LEGACY_KERNELS

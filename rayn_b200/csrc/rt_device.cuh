@@ -114,6 +114,13 @@ struct DevScene {
   RaynCamera cam;
   RaynVolume vol;
   RaynRenderConsts rc;
+  // derived at upload (api.cu::derive_scene_tables): the analytic spheres and the SDF hitables as compact lists in insertion
+  // order, so that the shading kernels neither walk all hitables testing `kind` nor index 40-byte descriptors per lane
+  int32_t n_sph, n_sdf, sph_moving, pad_;
+  int32_t sph_idx[RAYN_MAX_HITABLES];  // hitable index of sphere k
+  int32_t sdf_idx[RAYN_MAX_HITABLES];  // hitable index of SDF ordinal j
+  int32_t hit_ord[RAYN_MAX_HITABLES];  // hitable i is the hit_ord[i]-th sphere / SDF
+  float4 sph[RAYN_MAX_HITABLES];       // centre.xyz, radius of sphere k (a moving sphere keeps its t = 0 centre here)
 };
 
 // the `hit_threshold_at` closure of film.rs:540-551
@@ -294,6 +301,21 @@ RT_D float sphere_occluded_seg(const RaynHitable& h, f3 start, f3 dir, float dis
   bool valid = (mn > 0.001f) && (t1 <= dist) && desc_pos;
   return valid ? 0.0f : 1.0f;
 }
+// The same for a STATIC sphere given as (centre, radius).  sqrt is skipped when the discriminant is not positive (or NaN):
+// `valid` is false then whatever the root would have been, so the result is the same 1.0.
+RT_D float sphere_occluded_seg_static(const float4 cr, f3 start, f3 dir, float dist) {
+  const f3 oc = start - mk3(cr.x, cr.y, cr.z);
+  const float b = dot(oc, dir);
+  const float c = mag_sq(oc) - cr.w * cr.w;
+  const float descrim = b * b - c;
+  if (!(descrim > 0.0f)) return 1.0f;
+  const float desc_sqrt = sqrtf(descrim);
+  const float t1 = -b - desc_sqrt;
+  const float t2 = -b + desc_sqrt;
+  const float mn = dm::min(t1, t2);
+  const bool valid = (mn > 0.001f) && (t1 <= dist);
+  return valid ? 0.0f : 1.0f;
+}
 RT_D float sphere_occluded(const RaynHitable& h, f3 start, f3 end, float time0) {  // :24-46
   f3 dir = end - start;
   float dist = mag(dir);
@@ -323,6 +345,24 @@ RT_D float sphere_hit(const RaynHitable& h, f3 ro, f3 rd, float t_max, float tim
   bool t2_valid = (t2 > 0.0001f) && (t2 <= t_max) && desc_pos;
   bool take_t1 = (t1 < t2) && t1_valid;
   float t = take_t1 ? t1 : t2;
+  return (t1_valid || t2_valid) ? t : 3.40282347e+38f;
+}
+
+// Sphere::hit for a STATIC sphere given as (centre, radius): no root is taken when the discriminant is not positive (or NaN),
+// both candidates are invalid then and the result is the same f32::MAX.
+RT_D float sphere_hit_static(const float4 cr, f3 ro, f3 rd, float t_max) {
+  const f3 oc = ro - mk3(cr.x, cr.y, cr.z);
+  const float b = dot(oc, rd);
+  const float c = mag_sq(oc) - cr.w * cr.w;
+  const float descrim = b * b - c;
+  if (!(descrim > 0.0f)) return 3.40282347e+38f;
+  const float desc_sqrt = sqrtf(descrim);
+  const float t1 = -b - desc_sqrt;
+  const bool t1_valid = (t1 > 0.0001f) && (t1 <= t_max);
+  const float t2 = -b + desc_sqrt;
+  const bool t2_valid = (t2 > 0.0001f) && (t2 <= t_max);
+  const bool take_t1 = (t1 < t2) && t1_valid;
+  const float t = take_t1 ? t1 : t2;
   return (t1_valid || t2_valid) ? t : 3.40282347e+38f;
 }
 

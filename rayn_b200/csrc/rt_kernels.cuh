@@ -114,24 +114,25 @@ RT_D void warp_add_partial(unsigned long long* ctr, int v) {
   const int s = __reduce_add_sync(m, v);
   if ((int)(threadIdx.x & 31) == __ffs(m) - 1 && s) atomicAdd(ctr, (unsigned long long)s);
 }
-RT_D void warp_add(unsigned long long* ctr, int v) {
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+RT_D void warp_add(unsigned long long* ctr, int v) {  // full warp; one REDUX instead of a five-step shuffle tree
+  v = __reduce_add_sync(0xffffffffu, v);
   if ((threadIdx.x & 31) == 0 && v) atomicAdd(ctr, (unsigned long long)v);
 }
 
-// The head of the closest-hit fold (hitable.rs:177-198): t_max = 2 * WORLD_RADIUS (film.rs:556), then the analytic spheres
-// [0, pre_n) that precede the first SDF hitable, in insertion order.  Run by the kernel that PRODUCES the ray (origin and
-// direction are in registers there), which removes one gather of every live ray per depth.  Static spheres only: a moving
-// sphere is evaluated at the time of lane 0 of the extend packet, which is not known before compaction (k_extend_spheres
-// handles that case).
-RT_D void fold_head(const DevScene& sc, int pre_n, f3 o, f3 d, float* closest, int* id) {
+// The head of the closest-hit fold (hitable.rs:177-198): t_max = 2 * WORLD_RADIUS (film.rs:556), then the first n_fold analytic
+// spheres of the scene's compact sphere list (DevScene::sph, insertion order) - the spheres that precede the first SDF
+// hitable, or ALL spheres for scenes whose single SDF is marched last (api.cu: fold_all; proof at k_extend_march).  Run by
+// the kernel that PRODUCES the ray (origin and direction are in registers there), which removes one gather of every live
+// ray per depth.  Static spheres only: a moving sphere is evaluated at the time of lane 0 of the extend packet, which is
+// not known before compaction (k_extend_spheres handles that case).
+RT_D void fold_head(const DevScene& sc, int n_fold, f3 o, f3 d, float* closest, int* id) {
   float c = sc.rc.world_radius * 2.0f;
   int best = -1;
-  for (int k = 0; k < pre_n; ++k) {
-    const float t = sphere_hit(sc.hit[k], o, d, c, 0.0f);
+  for (int k = 0; k < n_fold; ++k) {
+    const float t = sphere_hit_static(sc.sph[k], o, d, c);
     if (t < c) {
       c = t;
-      best = k;
+      best = sc.sph_idx[k];
     }
   }
   *closest = c;
@@ -310,7 +311,7 @@ __global__ void __launch_bounds__(256) k_extend_spheres(const __grid_constant__ 
     float time0 = o4.w;
     if (moving && (i & 3)) time0 = pb.o_time[(size_t)ts * pb.R + pb.q_live[(size_t)ts * pb.R + (i & ~3)]].w;
     for (int k = first; k < last; ++k) {
-      const float t = sphere_hit(sc.hit[k], o, d, closest, time0);
+      const float t = moving ? sphere_hit(sc.hit[k], o, d, closest, time0) : sphere_hit_static(sc.sph[sc.hit_ord[k]], o, d, closest);
       if (t < closest) {
         closest = t;
         id = k;
@@ -331,6 +332,20 @@ __global__ void __launch_bounds__(256) k_extend_spheres(const __grid_constant__ 
 // depends only on its own ray, so the order in which slots pick up work cannot change any output bit.
 // The per-ray traffic is the algorithmic minimum: read float4 o+time, float4 d+closest (32 B), write
 // t + key (8 B) when this SDF is the new closest hit.
+//
+// spheres_first != 0 (api.cu: fold_all): the producing kernel has already folded in EVERY analytic sphere, also those that
+// follow this SDF in insertion order, and this march runs against the nearest of them.  That is the reference's fold
+// (hitable.rs:177-198: in insertion order, strict `t < closest`, so the first index wins a tie) provided that
+//  (1) a march's t never decreases - true for the Mandelbox, whose estimate sqrt(m) / |dr| is >= 0 or NaN - and
+//  (2) a tie between this SDF and a sphere is resolved by index: the SDF wins exactly when the sphere comes later.
+// Proof.  A sphere offers a candidate r* that does not depend on the bound it is tested against (sphere.rs:48-72: the bound only
+// invalidates roots beyond it) and is accepted iff r* < closest, so the fold is a running strict minimum.  Let c0 be the minimum
+// over the spheres before the SDF, c' <= c0 over all spheres.  The march visits the same t_0, t_1, ... whatever its bound;
+// the bound only decides where it stops: the reference stops at the first i with (hit_i or t_i > c0), here at the first i'
+// with (hit_i' or t_i' > c').  If i' = i both return the same T, and T wins the reference's fold iff T < c0 and T <= every later
+// sphere's r*, which is `T < c'` or `T == c'` with c' owned by a later sphere.  If i' < i then c' < t_i' <= c0 (so c' belongs to
+// a later sphere) and t_i' is rejected here; the reference marches on to T = t_i >= t_i' > c' by (1) (or to NaN), so that later
+// sphere beats it there as well.  A NaN t is accepted by neither.
 // ------------------------------------------------------------------------------------------
 #define EXT_T 128
 #ifndef RAYN_MARCH_OCC
@@ -338,7 +353,8 @@ __global__ void __launch_bounds__(256) k_extend_spheres(const __grid_constant__ 
 #endif
 template <int V>
 __global__ void __launch_bounds__(EXT_T, RAYN_MARCH_OCC) k_extend_march(const __grid_constant__ DevScene sc, const PassBufs pb, const Thr thr,
-                                                          const int hk, const int* __restrict__ batch_prefix, int* __restrict__ work_ctr) {
+                                                          const int hk, const int spheres_first, const int* __restrict__ batch_prefix,
+                                                          int* __restrict__ work_ctr) {
   const SdfK k = make_sdfk(sc.hit[hk], sc.one);  // fractal constants: kernel-parameter bank -> registers, once
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
@@ -441,7 +457,7 @@ __global__ void __launch_bounds__(EXT_T, RAYN_MARCH_OCC) k_extend_march(const __
     }
     if (done0 | done1) {
       if (done0 & (g0 >= 0)) {
-        if (t.x < closest.x) {  // hitable.rs:190-193
+        if (t.x < closest.x || (spheres_first && t.x == closest.x && pb.q_key[g0] > hk)) {  // hitable.rs:190-193 (+ tie rule above)
           pb.d_t[g0].w = t.x;
           pb.q_key[g0] = hk;
         }
@@ -449,7 +465,7 @@ __global__ void __launch_bounds__(EXT_T, RAYN_MARCH_OCC) k_extend_march(const __
         g0 = -1;
       }
       if (done1 & (g1 >= 0)) {
-        if (t.y < closest.y) {
+        if (t.y < closest.y || (spheres_first && t.y == closest.y && pb.q_key[g1] > hk)) {
           pb.d_t[g1].w = t.y;
           pb.q_key[g1] = hk;
         }
@@ -658,26 +674,26 @@ __global__ void __launch_bounds__(128, 8) k_shade_pre(const __grid_constant__ De
           f3 dir = lc.end_point - lc.start;
           const float max_dist = mag(dir);
           dir = dir / max_dist;
-          float v = 1.0f;  // analytic spheres first: product of {0,1} factors (hitable.rs:164-168)
-          for (int k = 0; k < sc.n_hit && v != 0.0f; ++k)
-            if (sc.hit[k].kind == RAYN_HITABLE_SPHERE) v = sphere_occluded_seg(sc.hit[k], lc.start, dir, max_dist, time0);
+          float v = 1.0f;  // analytic spheres first, in insertion order: product of {0,1} factors (hitable.rs:164-168)
+          if (sc.sph_moving) {
+            for (int k = 0; k < sc.n_sph && v != 0.0f; ++k) v = sphere_occluded_seg(sc.hit[sc.sph_idx[k]], lc.start, dir, max_dist, time0);
+          } else {
+            for (int k = 0; k < sc.n_sph && v != 0.0f; ++k) v = sphere_occluded_seg_static(sc.sph[k], lc.start, dir, max_dist);
+          }
           if (v == 0.0f) {
             vis &= ~(1u << bit);
             continue;
           }
-          int j = 0;  // SDF ordinal
-          for (int k = 0; k < sc.n_hit; ++k)
-            if (sc.hit[k].kind != RAYN_HITABLE_SPHERE) {
-              const unsigned am = __activemask();  // opportunistic warp aggregation of the queue append
-              const int leader = __ffs(am) - 1, ln = threadIdx.x & 31;
-              int base = 0;
-              if (ln == leader) base = atomicAdd(pb.seg_count + j, __popc(am));
-              base = __shfl_sync(am, base, leader);
-              const size_t slot = (size_t)j * pb.seg_cap + base + __popc(am & ((1u << ln) - 1u));
-              pb.seg_a[slot] = make_float4(lc.start.x, lc.start.y, lc.start.z, max_dist);
-              pb.seg_b[slot] = make_float4(dir.x, dir.y, dir.z, __int_as_float((int)(((unsigned)g << 4) | (unsigned)bit)));
-              ++j;
-            }
+          for (int j = 0; j < sc.n_sdf; ++j) {  // one shadow-segment queue per SDF hitable (ordinal j)
+            const unsigned am = __activemask();  // opportunistic warp aggregation of the queue append
+            const int leader = __ffs(am) - 1, ln = threadIdx.x & 31;
+            int base = 0;
+            if (ln == leader) base = atomicAdd(pb.seg_count + j, __popc(am));
+            base = __shfl_sync(am, base, leader);
+            const size_t slot = (size_t)j * pb.seg_cap + base + __popc(am & ((1u << ln) - 1u));
+            pb.seg_a[slot] = make_float4(lc.start.x, lc.start.y, lc.start.z, max_dist);
+            pb.seg_b[slot] = make_float4(dir.x, dir.y, dir.z, __int_as_float((int)(((unsigned)g << 4) | (unsigned)bit)));
+          }
         }
       }
       pb.vis[g] = vis;
@@ -840,7 +856,12 @@ __global__ void __launch_bounds__(128, 8) k_shade_post(const __grid_constant__ D
       const int bit = round * 4 + i;
       const float4 c4 = pb.lc_c[g * pb.lc_ns + bit];  // li * f * transmission and pdf, written by k_shade_pre
       const float occluded = (vis >> bit) & 1u ? 1.0f : 0.0f;
-      const f3 contrib = mk3(c4.x, c4.y, c4.z) * occluded / c4.w;  // :239 / :278
+      // :239 / :278 `li * f * occluded / pdf`.  An occluded or back-facing sample has a (+-0, +-0, +-0) numerator, and +-0 / pdf is
+      // that same +-0 for every pdf > 0: no division then (r02c profile: zero numerators send IEEE division down its slow
+      // path, 17 % of this kernel's instructions).  NaN numerators and pdf <= 0 / NaN take the division as before.
+      const f3 num = mk3(c4.x, c4.y, c4.z) * occluded;
+      const bool no_div = (num.x == 0.0f) & (num.y == 0.0f) & (num.z == 0.0f) & (c4.w > 0.0f);
+      const f3 contrib = no_div ? num : num / c4.w;
       if (round == 0)
         radiance = radiance + contrib * throughput * correction * vt;  // :91-92
       else

@@ -94,7 +94,8 @@ def test_three_operation_division_is_selected_only_after_its_exhaustive_check(or
     c, inp = small_config(3, (48, 48), 2, 4)
     o, _ = oracle.render(c["world"], c["camera"], inp, (16, 16), c["integrator"], TR)
     sdf_index = [i for i, h in enumerate(c["world"].hitables.items) if hasattr(h, "sdf")][0]
-    for flags, want in ((0, (4,)), (L.FLAG_NO_DIV3, (1,))):
+    # (third case: RAYN_FLAG_NO_FOLD_ALL keeps the closest-hit fold in insertion order instead of marching the Mandelbox last)
+    for flags, want in ((0, (4,)), (L.FLAG_NO_DIV3, (1,)), (L.FLAG_NO_FOLD_ALL, (4,))):
         r = Renderer(0, flags=flags)
         try:
             r.upload_scene(c["world"], c["camera"])
