@@ -66,6 +66,7 @@ struct RaynContext {
   int64_t alloc_paths = 0, alloc_q = 0, alloc_seg = 0;
   int alloc_lc_ns = 0;
   int alloc_tiles = 0;
+  int64_t alloc_segcnt = 0;  // ints in PassBufs::seg_cnt
   size_t pass_bytes = 0;
   PassBufs pb;
   int* d_tile_ids = nullptr;
@@ -156,7 +157,7 @@ static void free_pass(RaynContext* c) {
   cudaFree(c->d_tile_ids);
   cudaFree(c->d_batch_prefix);
   c->d_batch_prefix = nullptr;
-  cudaFree(p.nrm), cudaFree(p.vis), cudaFree(p.seg_a), cudaFree(p.seg_b), cudaFree(p.lc_c), cudaFree(p.lc_t);
+  cudaFree(p.nrm), cudaFree(p.vis), cudaFree(p.seg_a), cudaFree(p.seg_b), cudaFree(p.lc_c), cudaFree(p.lc_t), cudaFree(p.seg_cnt);
   unsigned long long* counters = p.counters;
   memset(&p, 0, sizeof p);
   p.counters = counters;
@@ -164,6 +165,7 @@ static void free_pass(RaynContext* c) {
   c->alloc_paths = c->alloc_q = c->alloc_seg = 0;
   c->alloc_lc_ns = 0;
   c->alloc_tiles = 0;
+  c->alloc_segcnt = 0;
   c->pass_bytes = 0;
 }
 
@@ -176,7 +178,9 @@ static size_t pass_bytes_per_path(int R, int QS, int seg_per_path, int lc_ns) {
 static int32_t ensure_pass(RaynContext* ctx, int n_tiles, int R, int QS, int seg_per_path_total, int n_sdf, int lc_ns) {
   const int64_t need_paths = (int64_t)n_tiles * R, need_q = (int64_t)n_tiles * QS;
   const int64_t need_seg = need_paths * seg_per_path_total;  // all SDF queues together
-  if (need_paths <= ctx->alloc_paths && need_q <= ctx->alloc_q && n_tiles <= ctx->alloc_tiles && need_seg <= ctx->alloc_seg && lc_ns <= ctx->alloc_lc_ns)
+  const int64_t need_segcnt = (int64_t)n_tiles * ((QS + SEG_SLOTS - 1) / SEG_SLOTS) * RAYN_MAX_HITABLES;
+  if (need_paths <= ctx->alloc_paths && need_q <= ctx->alloc_q && n_tiles <= ctx->alloc_tiles && need_seg <= ctx->alloc_seg && lc_ns <= ctx->alloc_lc_ns &&
+      need_segcnt <= ctx->alloc_segcnt)
     return RAYN_OK;
   free_pass(ctx);
   PassBufs& p = ctx->pb;
@@ -205,6 +209,8 @@ static int32_t ensure_pass(RaynContext* ctx, int n_tiles, int R, int QS, int seg
   PASS_ALLOC(p.bin_start, (size_t)n_tiles * (RAYN_MAX_HITABLES + 1) * sizeof(int));
   PASS_ALLOC(ctx->d_tile_ids, n_tiles * sizeof(int));
   PASS_ALLOC(ctx->d_batch_prefix, ((size_t)n_tiles + 1) * sizeof(int));
+  PASS_ALLOC(p.seg_cnt, need_segcnt * sizeof(int));
+  ctx->alloc_segcnt = need_segcnt;
   PASS_ALLOC(p.nrm, need_paths * sizeof(float4));
   PASS_ALLOC(p.vis, need_paths * sizeof(uint32_t));
   if (need_seg > 0) {
@@ -526,7 +532,7 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
   int np = 32;
   while (np < spp) np <<= 1;
   const int wpc = resolve_warps_per_cta(np);
-  if (wpc < 1 || np > 65536) return fail(ctx, RAYN_ERR_UNSUPPORTED, "spp = %d: the film resolve holds 12 B per sample of a pixel in shared memory (max 16384 spp)", spp);
+  if (wpc < 1 || np > 65536) return fail(ctx, RAYN_ERR_UNSUPPORTED, "spp = %d: the film resolve holds 6 B per sample of a pixel in shared memory (max 32768 spp)", spp);
   const int R = (int)R64, QS = R + 4 * n_hit;
   CU(cudaSetDevice(ctx->device));
   {  // a previous call that failed half way through a graph capture must not leave the stream capturing
@@ -689,6 +695,7 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
     }
     ctx->stats.passes++;
     const dim3 g_paths((R + 255) / 256, nt), g_shade((QS + 127) / 128, nt);
+    const int nseg = (QS + SEG_SLOTS - 1) / SEG_SLOTS;  // segments per tile of the queue kernels
     timed_begin(ctx, RAYN_K_RAYGEN);
     k_raygen<<<g_paths, 256, 0, st>>>(ctx->scene, fr, pb, n_fold);
     timed_end(ctx, RAYN_K_RAYGEN);
@@ -728,8 +735,9 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
         }
       }
       timed_begin(ctx, RAYN_K_BIN);
-      k_bin<<<nt, BIN_T, 0, st>>>(pb, n_hit);
-      timed_end(ctx, RAYN_K_BIN);
+      k_bin_count<<<dim3(nseg, nt), BIN_T, 0, st>>>(pb, n_hit, nseg);
+      k_bin_scatter<<<dim3(nseg, nt), BIN_T, 0, st>>>(pb, n_hit, nseg);
+      timed_end(ctx, RAYN_K_BIN, 2);
       if (ctx->qlog_enabled) {
         h_nslots.resize(nt);
         h_slots.resize((size_t)nt * QS);
@@ -777,8 +785,9 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
       }
       if (depth < mb) {
         timed_begin(ctx, RAYN_K_COMPACT);
-        k_compact<<<nt, CMP_T, 0, st>>>(pb);
-        timed_end(ctx, RAYN_K_COMPACT);
+        k_compact_count<<<dim3(nseg, nt), CMP_T, 0, st>>>(pb, nseg);
+        k_compact_scatter<<<dim3(nseg, nt), CMP_T, 0, st>>>(pb, nseg);
+        timed_end(ctx, RAYN_K_COMPACT, 2);
       }
     }
     timed_begin(ctx, RAYN_K_RESOLVE);

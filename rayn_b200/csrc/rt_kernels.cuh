@@ -19,9 +19,9 @@
 //   `for x { for y { for samp { 4 lanes } } }` (film.rs:456-464).
 //
 // Kernel sequence of a pass: k_raygen, then per depth
-//   k_scan_live -> k_extend_spheres / k_extend_march<V> (fold order of hitable.rs:177-198) -> k_bin
+//   k_scan_live -> k_extend_spheres / k_extend_march<V> (fold order of hitable.rs:177-198) -> k_bin_count, k_bin_scatter
 //   -> k_normals<V> (one per SDF hitable) -> k_shade_pre -> k_shadow<V> (one per SDF hitable)
-//   -> k_shade_post -> k_compact;  finally k_resolve.
+//   -> k_shade_post -> k_compact_count, k_compact_scatter;  finally k_resolve.
 // The two march kernels and k_normals evaluate the distance field on TWO points per thread with the packed
 // f32x2 arithmetic of sm_100a (rt_sdf2.cuh).
 #pragma once
@@ -69,6 +69,7 @@ struct PassBufs {
   float4* lc_c;       // [paths * lc_ns] unoccluded light contribution c.xyz and its denominator (pdf), per light sample of this depth
   float* lc_t;        // [paths * 8] volume rounds only: transmission to the scatter point (integrator.rs:122-126)
   int lc_ns;          // light samples per path per depth: 4, or 4 * (1 + vm) with volumetrics
+  int* seg_cnt;       // [n_tiles * nseg * RAYN_MAX_HITABLES] scratch of the segmented queue kernels (k_bin_*, k_compact_*)
 };
 
 enum { CNT_EXTEND_RAYS = 0, CNT_SHADE_LANES = 1, CNT_SHADOW_RAYS = 2, CNT_EVALS_EXTEND = 3, CNT_EVALS_SHADOW = 4,
@@ -183,45 +184,74 @@ __global__ void __launch_bounds__(256) k_raygen(const __grid_constant__ DevScene
 // tile; chunks of BIN_T rays; per-warp __match_any_sync ranks + cross-warp offsets in smem.
 // ------------------------------------------------------------------------------------------
 #define BIN_T 1024
-__global__ void __launch_bounds__(BIN_T) k_bin(const PassBufs pb, const int n_hit) {
-  const int ts = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = BIN_T / 32;
+#define SEG_SLOTS 32768  // rays / slots one CTA of the per-tile queue kernels (bin, compact) walks
+// Two kernels, grid (segments, tiles): at 4096 spp a tile holds 1 Mi rays and a pass only 96 tiles, so one CTA per tile
+// (round 1 and 2a) left a third of the SMs idle and walked 1024 chunks serially - the 8-GPU weak-scaled config-3 run lost 5 %
+// of its frame here.  A tile's live list is cut into SEG_SLOTS-ray segments; k_bin_count leaves per-segment per-object counts in
+// HBM, k_bin_scatter turns them into the segment's write cursors and scatters.  The partition stays stable (segments are in
+// order, a segment is scattered in order), so the queue is the same as the single-CTA one, bit for bit.
+__global__ void __launch_bounds__(BIN_T) k_bin_count(const PassBufs pb, const int n_hit, const int nseg) {
+  const int seg = blockIdx.x, ts = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
   const int n = pb.n_live[ts];
   __shared__ int cnt[RAYN_MAX_HITABLES];
+  const int* __restrict__ qk = pb.q_key + (size_t)ts * pb.R;  // per path
+  const int* __restrict__ ql = pb.q_live + (size_t)ts * pb.R;
+  if (tid < RAYN_MAX_HITABLES) cnt[tid] = 0;
+  if (tid == 0 && seg == 0 && n) atomicAdd(pb.counters + CNT_EXTEND_RAYS, (unsigned long long)n);  // rays through the closest-hit stage
+  __syncthreads();
+  const int lo = seg * SEG_SLOTS, hi = min(n, lo + SEG_SLOTS);
+  for (int base = lo; base < hi; base += BIN_T) {
+    const int i = base + tid;
+    const int key = i < hi ? qk[ql[i]] : -1;
+    const unsigned m = __match_any_sync(0xffffffffu, key);
+    if (key >= 0 && (m & ((1u << lane) - 1)) == 0) atomicAdd(&cnt[key], __popc(m));
+  }
+  __syncthreads();
+  if (tid < n_hit) pb.seg_cnt[((size_t)ts * nseg + seg) * RAYN_MAX_HITABLES + tid] = cnt[tid];
+}
+__global__ void __launch_bounds__(BIN_T) k_bin_scatter(const PassBufs pb, const int n_hit, const int nseg) {
+  const int seg = blockIdx.x, ts = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = BIN_T / 32;
+  const int n = pb.n_live[ts];
+  const int lo = seg * SEG_SLOTS, hi = min(n, lo + SEG_SLOTS);
+  if (lo >= n && seg > 0) return;  // nothing to scatter; segment 0 still publishes the (possibly empty) bin table
+  __shared__ int cnt[RAYN_MAX_HITABLES];        // whole-tile counts
+  __shared__ int before[RAYN_MAX_HITABLES];     // counts of the segments before this one
   __shared__ int start[RAYN_MAX_HITABLES + 1];
   __shared__ int running[2][RAYN_MAX_HITABLES];
   __shared__ int wcnt[2][NW][RAYN_MAX_HITABLES];
-  const int* __restrict__ qk = pb.q_key + (size_t)ts * pb.R;  // per path
+  const int* __restrict__ qk = pb.q_key + (size_t)ts * pb.R;
   const int* __restrict__ ql = pb.q_live + (size_t)ts * pb.R;
   int* __restrict__ qs = pb.q_shade + (size_t)ts * pb.QS;
-  if (tid < RAYN_MAX_HITABLES) cnt[tid] = 0;
-  if (tid == 0 && n) atomicAdd(pb.counters + CNT_EXTEND_RAYS, (unsigned long long)n);  // rays through the closest-hit stage
-  __syncthreads();
-  for (int base = 0; base < n; base += BIN_T) {  // pass A: per-object counts
-    const int i = base + tid;
-    const int key = i < n ? qk[ql[i]] : -1;
-    const unsigned m = __match_any_sync(0xffffffffu, key);
-    if (key >= 0 && (m & ((1u << lane) - 1)) == 0) atomicAdd(&cnt[key], __popc(m));
+  if (tid < n_hit) {
+    const int used = (n + SEG_SLOTS - 1) / SEG_SLOTS;
+    int tot = 0, bef = 0;
+    for (int sg = 0; sg < used; ++sg) {
+      const int c = pb.seg_cnt[((size_t)ts * nseg + sg) * RAYN_MAX_HITABLES + tid];
+      if (sg < seg) bef += c;
+      tot += c;
+    }
+    cnt[tid] = tot, before[tid] = bef;
   }
   __syncthreads();
   if (tid == 0) {
     int off = 0;
     for (int o = 0; o < n_hit; ++o) {
       start[o] = off;
-      running[0][o] = off;
+      running[0][o] = off + before[o];
       off += (cnt[o] + 3) & ~3;  // every bin padded to a multiple of 4 (hitable.rs:100-111)
     }
     start[n_hit] = off;
-    pb.n_slots[ts] = off;
+    if (seg == 0) pb.n_slots[ts] = off;
   }
   __syncthreads();
-  if (tid <= n_hit) pb.bin_start[ts * (RAYN_MAX_HITABLES + 1) + tid] = start[tid];
-  // pass B: stable scatter, ONE barrier per 1024-ray chunk (double-buffered warp counts and bin cursors)
+  if (seg == 0 && tid <= n_hit) pb.bin_start[ts * (RAYN_MAX_HITABLES + 1) + tid] = start[tid];
+  // stable scatter of this segment, ONE barrier per 1024-ray chunk (double-buffered warp counts and bin cursors)
   int buf = 0;
-  for (int base = 0; base < n; base += BIN_T, buf ^= 1) {
+  for (int base = lo; base < hi; base += BIN_T, buf ^= 1) {
     const int i = base + tid;
-    const int id = i < n ? ql[i] : -1;
-    const int key = i < n ? qk[id] : -1;
+    const int id = i < hi ? ql[i] : -1;
+    const int key = i < hi ? qk[id] : -1;
     unsigned mine = 0;
     for (int k = 0; k < n_hit; ++k) {
       const unsigned b = __ballot_sync(0xffffffffu, key == k);
@@ -240,7 +270,7 @@ __global__ void __launch_bounds__(BIN_T) k_bin(const PassBufs pb, const int n_hi
       running[buf ^ 1][tid] = tot;
     }
   }
-  if (tid < n_hit)
+  if (seg == 0 && tid < n_hit)
     for (int k = start[tid] + cnt[tid]; k < start[tid + 1]; ++k) qs[k] = -1;  // Ray::new_invalid padding
 }
 
@@ -912,29 +942,57 @@ __global__ void __launch_bounds__(128, 8) k_shade_post(const __grid_constant__ D
 // no observable effect: add_hits drops invalid lanes, hitable.rs:204.)
 // ------------------------------------------------------------------------------------------
 #define CMP_T 1024
-__global__ void __launch_bounds__(CMP_T) k_compact(const PassBufs pb) {
-  const int ts = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// grid (segments, tiles) like k_bin_*: survivors per SEG_SLOTS-slot segment, then every segment writes at the sum of the counts
+// before it - the same order-preserving compaction as one CTA walking the whole tile.
+__global__ void __launch_bounds__(CMP_T) k_compact_count(const PassBufs pb, const int nseg) {
+  const int seg = blockIdx.x, ts = blockIdx.y, tid = threadIdx.x;
+  const int n = pb.n_slots[ts];
+  const int* __restrict__ qs = pb.q_shade + (size_t)ts * pb.QS;
+  const int lo = seg * SEG_SLOTS, hi = min(n, lo + SEG_SLOTS);
+  int c = 0;
+  for (int i = lo + tid; i < hi; i += CMP_T) c += qs[i] >= 0 ? 1 : 0;
+  c = __reduce_add_sync(0xffffffffu, c);
+  __shared__ int tot;
+  if (tid == 0) tot = 0;
+  __syncthreads();
+  if ((tid & 31) == 0 && c) atomicAdd(&tot, c);
+  __syncthreads();
+  if (tid == 0) pb.seg_cnt[((size_t)ts * nseg + seg) * RAYN_MAX_HITABLES] = tot;
+}
+__global__ void __launch_bounds__(CMP_T) k_compact_scatter(const PassBufs pb, const int nseg) {
+  const int seg = blockIdx.x, ts = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = CMP_T / 32;
   const int n = pb.n_slots[ts];
+  const int lo = seg * SEG_SLOTS, hi = min(n, lo + SEG_SLOTS);
+  if (lo >= n && seg > 0) return;
   const int* __restrict__ qs = pb.q_shade + (size_t)ts * pb.QS;
   int* __restrict__ ql = pb.q_live + (size_t)ts * pb.R;
   __shared__ int wtot[2][NW];
   __shared__ int running[2];
-  if (tid == 0) running[0] = 0;
+  if (tid == 0) {
+    const int used = (n + SEG_SLOTS - 1) / SEG_SLOTS;
+    int bef = 0, tot = 0;
+    for (int sg = 0; sg < used; ++sg) {
+      const int c = pb.seg_cnt[((size_t)ts * nseg + sg) * RAYN_MAX_HITABLES];
+      if (sg < seg) bef += c;
+      tot += c;
+    }
+    running[0] = bef;
+    if (seg == 0) pb.n_live[ts] = tot;
+  }
+  __syncthreads();
   int buf = 0;
-  for (int base = 0; base < n; base += CMP_T, buf ^= 1) {  // one barrier per 1024-slot chunk
+  for (int base = lo; base < hi; base += CMP_T, buf ^= 1) {  // one barrier per 1024-slot chunk
     const int i = base + tid;
-    const int id = i < n ? qs[i] : -1;
+    const int id = i < hi ? qs[i] : -1;
     const unsigned b = __ballot_sync(0xffffffffu, id >= 0);
     if (lane == 0) wtot[buf][warp] = __popc(b);
     __syncthreads();
     int off = running[buf] + __popc(b & ((1u << lane) - 1));
     for (int w = 0; w < warp; ++w) off += wtot[buf][w];
     if (id >= 0) ql[off] = id;
-    if (tid == CMP_T - 1) running[buf ^ 1] = off + (id >= 0 ? 1 : 0);  // last thread's end offset = new total
+    if (tid == CMP_T - 1) running[buf ^ 1] = off + (id >= 0 ? 1 : 0);  // last thread's end offset = new running total
   }
-  __syncthreads();
-  if (tid == 0) pb.n_live[ts] = running[buf];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -948,7 +1006,9 @@ __global__ void __launch_bounds__(CMP_T) k_compact(const PassBufs pb) {
 // HBM; one warp per pixel puts 4-16x more pixels in flight per SM.)
 // ------------------------------------------------------------------------------------------
 #define RES_MAX_WARPS 8
-__host__ __device__ inline size_t resolve_smem_per_warp(int np) { return (size_t)np * (2 * sizeof(uint32_t) + 2 * sizeof(uint16_t)); }
+// per warp: one key + one index per sample (the two orders are resolved one after the other in the same arrays) and a
+// 32-entry staging buffer for the ordered sums
+__host__ __device__ inline size_t resolve_smem_per_warp(int np) { return (size_t)np * (sizeof(uint32_t) + sizeof(uint16_t)) + 32 * sizeof(float4); }
 static inline int resolve_warps_per_cta(int np) {
   int w = (int)((size_t)200 * 1024 / resolve_smem_per_warp(np));
   return w < 1 ? 0 : (w > RES_MAX_WARPS ? RES_MAX_WARPS : w);
@@ -971,16 +1031,85 @@ RT_D void warp_bitonic(uint32_t* key, uint16_t* val, int np, int lane) {
     }
   }
 }
+// keys of one order into shared memory; returns the number of valid keys, *unordered != 0 if they are not ascending already.
+// WHICH = 0: depth-0 slot + 1 of receives_light hits (WorldNormal / Alpha order, integrator.rs:161-169);
+// WHICH = 1: (depth, slot) at termination (Color / Background order, integrator.rs:178-203).
+template <int WHICH>
+RT_D int resolve_keys(const float4* __restrict__ nrm0, const uint32_t* __restrict__ term, int spp, int np, int lane, uint32_t* key, uint16_t* val,
+                      int* unordered) {
+  int n = 0, bad = 0;
+  uint32_t prev = 0;  // last key of the previous 32-chunk (lane 31), for the sortedness test
+  for (int base = 0; base < np; base += 32) {
+    const int i = base + lane;
+    uint32_t k = 0xffffffffu;
+    if (i < spp) {
+      if (WHICH == 0) {
+        const uint32_t s0 = __float_as_uint(nrm0[i].w);
+        if (s0) k = s0;
+      } else {
+        const uint32_t t = term[i];
+        if (t >> 30) k = t & 0x3fffffffu;
+      }
+    }
+    key[i] = k;
+    val[i] = (uint16_t)i;
+    n += __popc(__ballot_sync(0xffffffffu, k != 0xffffffffu));
+    uint32_t pk = __shfl_up_sync(0xffffffffu, k, 1);
+    if (lane == 0) pk = prev;
+    bad |= (i > 0) && pk > k;
+    prev = __shfl_sync(0xffffffffu, k, 31);
+  }
+  *unordered = __any_sync(0xffffffffu, bad);
+  return n;
+}
+// Strictly sequential float sums over the first n entries of val[] (the reference's accumulation order), channel lanes
+// [0, n_lanes): lane l adds component l % 3 of src[val[i]] when the entry's class matches (`want` < 0: every entry).  The
+// payload of 32 entries at a time is gathered by the whole warp (32 loads in flight, the next chunk already requested),
+// staged in shared memory and then read back in order by the channel lanes: the sum itself stays one dependent FADD chain per
+// channel, its operands no longer arrive one L2 round trip at a time (round-2 finding: at 4096 spp the per-lane gathers made
+// this kernel 12 % of a frame).
+RT_D float resolve_sum(const float4* __restrict__ src, const uint32_t* __restrict__ term, const uint16_t* val, int n, int lane, int n_lanes,
+                       int want, float4* stage) {
+  auto fetch = [&](int base) {
+    float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const int i = base + lane;
+    if (i < n) {
+      const int p = val[i];
+      v = src[p];
+      v.w = term ? __uint_as_float(term[p] >> 30) : 0.0f;
+    }
+    return v;
+  };
+  const int ch = lane % 3;
+  float acc = 0.0f;
+  float4 cur = fetch(0);
+  for (int base = 0; base < n; base += 32) {
+    const float4 nxt = fetch(base + 32);
+    stage[lane] = cur;
+    __syncwarp();
+    const int m = min(32, n - base);
+    if (lane < n_lanes) {
+#pragma unroll 8
+      for (int j = 0; j < m; ++j) {
+        const float4 e = stage[j];
+        const float x = ch == 0 ? e.x : (ch == 1 ? e.y : e.z);
+        acc += (want < 0 || (int)__float_as_uint(e.w) == want) ? x : 0.0f;
+      }
+    }
+    __syncwarp();
+    cur = nxt;
+  }
+  return acc;
+}
 __global__ void __launch_bounds__(RES_MAX_WARPS * 32) k_resolve(const DevFrame fr, const PassBufs pb, float* __restrict__ color,
                                                                  float* __restrict__ alpha, float* __restrict__ background,
                                                                  float* __restrict__ normal, const int np, const int wpc) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* mine = smem_raw + (size_t)warp * resolve_smem_per_warp(np);
-  uint32_t* keyA = reinterpret_cast<uint32_t*>(mine);  // depth-0 slot + 1 of receives_light hits: WorldNormal / Alpha order (integrator.rs:161-169)
-  uint32_t* keyB = keyA + np;                          // (depth, slot) at termination: Color / Background order (integrator.rs:178-203)
-  uint16_t* valA = reinterpret_cast<uint16_t*>(keyB + np);
-  uint16_t* valB = valA + np;
+  float4* stage = reinterpret_cast<float4*>(mine);
+  uint32_t* key = reinterpret_cast<uint32_t*>(stage + 32);
+  uint16_t* val = reinterpret_cast<uint16_t*>(key + np);
   const int ts = blockIdx.y, pl = blockIdx.x * wpc + warp;
   const TileGeom tg = tile_geom(fr, pb.tile_ids[ts]);
   if (pl >= tg.tw * tg.th) return;  // warp-uniform
@@ -991,52 +1120,28 @@ __global__ void __launch_bounds__(RES_MAX_WARPS * 32) k_resolve(const DevFrame f
   const float4* __restrict__ rad = pb.rad + g0;
   const uint32_t* __restrict__ term = pb.term + g0;
   const float div = (float)fr.spp;
-  int nA = 0, nB = 0, badA = 0, badB = 0;
-  uint32_t prevA = 0, prevB = 0;  // last key of the previous 32-chunk (lane 31), for the sortedness test
-  for (int base = 0; base < np; base += 32) {
-    const int i = base + lane;
-    uint32_t ka = 0xffffffffu, kb = 0xffffffffu;
-    if (i < fr.spp) {
-      const uint32_t s0 = __float_as_uint(nrm0[i].w), t = term[i];
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(rad + i));
-      if (s0) ka = s0;
-      if (t >> 30) kb = t & 0x3fffffffu;
-    }
-    keyA[i] = ka, keyB[i] = kb;
-    valA[i] = valB[i] = (uint16_t)i;
-    nA += __popc(__ballot_sync(0xffffffffu, ka != 0xffffffffu));
-    nB += __popc(__ballot_sync(0xffffffffu, kb != 0xffffffffu));
-    uint32_t pa = __shfl_up_sync(0xffffffffu, ka, 1), pbk = __shfl_up_sync(0xffffffffu, kb, 1);
-    if (lane == 0) pa = prevA, pbk = prevB;
-    badA |= (base + lane > 0) && pa > ka;
-    badB |= (base + lane > 0) && pbk > kb;
-    prevA = __shfl_sync(0xffffffffu, ka, 31), prevB = __shfl_sync(0xffffffffu, kb, 31);
+  int unordered;
+  // WorldNormal xyz (lanes 0-2) and Alpha in depth-0 slot order
+  const int nA = resolve_keys<0>(nrm0, term, fr.spp, np, lane, key, val, &unordered);
+  __syncwarp();
+  if (unordered) warp_bitonic(key, val, np, lane);
+  __syncwarp();
+  {
+    const float acc = resolve_sum(nrm0, nullptr, val, nA, lane, 3, -1, stage);
+    if (lane < 3 && normal) normal[3 * pix + lane] = acc / div;
+    if (lane == 3 && alpha) alpha[pix] = (float)nA / div;  // Alpha(1.0) per depth-0 receives_light sample: a sum of nA ones is nA exactly
   }
   __syncwarp();
-  if (__any_sync(0xffffffffu, badA)) warp_bitonic(keyA, valA, np, lane);
-  if (__any_sync(0xffffffffu, badB)) warp_bitonic(keyB, valB, np, lane);
+  // Color rgb (lanes 0-2) and Background rgb (lanes 3-5) in (depth, slot) order.  (A Color lane adds +0.0f for a Background
+  // entry and vice versa: exact no-ops, the accumulator can never be -0.)
+  const int nB = resolve_keys<1>(nrm0, term, fr.spp, np, lane, key, val, &unordered);
   __syncwarp();
-  // strictly sequential float sums in the reference's order.  lanes 0-2: WorldNormal xyz; 3-5: Color rgb; 6-8: Background rgb.
-  // (A Color lane adds +0.0f for a Background entry and vice versa: exact no-ops, the accumulator can never be -0.)
-  if (lane < 3) {
-    float acc = 0.0f;
-#pragma unroll 8
-    for (int i = 0; i < nA; ++i) acc += reinterpret_cast<const float*>(nrm0 + valA[i])[lane];
-    if (normal) normal[3 * pix + lane] = acc / div;
-  } else if (lane < 9) {
-    const int ch = (lane - 3) % 3;
-    const uint32_t want = lane < 6 ? TERM_COLOR : TERM_BACKGROUND;
-    float acc = 0.0f;
-#pragma unroll 8
-    for (int i = 0; i < nB; ++i) {
-      const int v = valB[i];
-      const float x = reinterpret_cast<const float*>(rad + v)[ch];
-      acc += (term[v] >> 30) == want ? x : 0.0f;
-    }
-    float* dst = lane < 6 ? color : background;
-    if (dst) dst[3 * pix + ch] = acc / div;
-  } else if (lane == 9) {
-    if (alpha) alpha[pix] = (float)nA / div;  // Alpha(1.0) per depth-0 receives_light sample: a sum of nA ones is nA exactly
+  if (unordered) warp_bitonic(key, val, np, lane);
+  __syncwarp();
+  {
+    const float acc = resolve_sum(rad, term, val, nB, lane, 6, lane < 3 ? (int)TERM_COLOR : (int)TERM_BACKGROUND, stage);
+    float* dst = lane < 3 ? color : background;
+    if (lane < 6 && dst) dst[3 * pix + lane % 3] = acc / div;
   }
 }
 
