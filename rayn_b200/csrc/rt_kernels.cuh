@@ -1006,40 +1006,84 @@ __global__ void __launch_bounds__(CMP_T) k_compact_scatter(const PassBufs pb, co
 // HBM; one warp per pixel puts 4-16x more pixels in flight per SM.)
 // ------------------------------------------------------------------------------------------
 #define RES_MAX_WARPS 8
-// per warp: one key + one index per sample (the two orders are resolved one after the other in the same arrays) and a
-// 32-entry staging buffer for the ordered sums
-__host__ __device__ inline size_t resolve_smem_per_warp(int np) { return (size_t)np * (sizeof(uint32_t) + sizeof(uint16_t)) + 32 * sizeof(float4); }
+#define RES_ROW 33                       // staging rows are 32 entries + 1 pad: the channel lanes read their rows bank-conflict free
+#define RES_STAGE_FLOATS (6 * RES_ROW + 2)  // staging buffer of the ordered sums: up to 6 channel rows
+// per warp: key[np] (by sample index), two index arrays (ping-pong of the radix sort), 256 histogram bins, the staging rows
+__host__ __device__ inline size_t resolve_smem_per_warp(int np) {
+  return (size_t)np * (sizeof(uint32_t) + 2 * sizeof(uint16_t)) + 256 * sizeof(int) + RES_STAGE_FLOATS * sizeof(float);
+}
 static inline int resolve_warps_per_cta(int np) {
   int w = (int)((size_t)200 * 1024 / resolve_smem_per_warp(np));
   return w < 1 ? 0 : (w > RES_MAX_WARPS ? RES_MAX_WARPS : w);
 }
-// in-warp bitonic sort of (key, val) ascending; np a power of two
-RT_D void warp_bitonic(uint32_t* key, uint16_t* val, int np, int lane) {
-  for (int k = 2; k <= np; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int p = lane; p < (np >> 1); p += 32) {
-        const int i = ((p & ~(j - 1)) << 1) | (p & (j - 1)), ixj = i | j;
-        const bool up = (i & k) == 0;
-        const uint32_t a = key[i], b = key[ixj];
-        if ((a > b) == up) {
-          key[i] = b, key[ixj] = a;
-          const uint16_t t = val[i];
-          val[i] = val[ixj], val[ixj] = t;
-        }
+// One warp sorts the n sample indices in src[] by key[index] ascending: LSD radix sort, 8 bits per pass, stable, passes whose
+// digit is the same for every key are skipped.  Returns the array that holds the result (src or tmp).  (The bitonic network it
+// replaces needed 78 dependent shared-memory stages at 4096 spp - 400 k cycles per pixel at two warps per scheduler.)
+RT_D uint16_t* warp_radix_sort(const uint32_t* key, uint16_t* src, uint16_t* tmp, int n, int lane, int* hist) {
+  const unsigned lt = (1u << lane) - 1u;
+  for (int shift = 0; shift < 32; shift += 8) {
+    for (int b = lane; b < 256; b += 32) hist[b] = 0;
+    __syncwarp();
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      if (i < n) atomicAdd(&hist[(key[src[i]] >> shift) & 255u], 1);
+    }
+    __syncwarp();
+    // exclusive scan of the 256 bins: lane l owns bins 8l .. 8l+7
+    int c[8], sum = 0;
+    bool uniform = false;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      c[q] = hist[8 * lane + q];
+      uniform |= c[q] == n;
+      sum += c[q];
+    }
+    if (__any_sync(0xffffffffu, uniform)) continue;  // every key has the same digit here: nothing to do
+    int incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    int run = incl - sum;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      hist[8 * lane + q] = run;
+      run += c[q];
+    }
+    __syncwarp();
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      const bool act = i < n;
+      const int v = act ? src[i] : 0;
+      const unsigned d = act ? ((key[v] >> shift) & 255u) : (256u + lane);  // inactive lanes: singleton groups
+      const unsigned m = __match_any_sync(0xffffffffu, d);
+      const int leader = __ffs(m) - 1;
+      int pos = 0;
+      if (act && lane == leader) {
+        pos = hist[d];
+        hist[d] = pos + __popc(m);
       }
+      pos = __shfl_sync(0xffffffffu, pos, leader) + __popc(m & lt);
+      if (act) tmp[pos] = (uint16_t)v;
       __syncwarp();
     }
+    uint16_t* t = src;
+    src = tmp;
+    tmp = t;
   }
+  return src;
 }
-// keys of one order into shared memory; returns the number of valid keys, *unordered != 0 if they are not ascending already.
+// keys of one order into shared memory (key[sample index]) and the indices of the samples that take part, in sample order,
+// into idx[]; returns their number, *unordered != 0 if their keys are not ascending already.
 // WHICH = 0: depth-0 slot + 1 of receives_light hits (WorldNormal / Alpha order, integrator.rs:161-169);
 // WHICH = 1: (depth, slot) at termination (Color / Background order, integrator.rs:178-203).
 template <int WHICH>
-RT_D int resolve_keys(const float4* __restrict__ nrm0, const uint32_t* __restrict__ term, int spp, int np, int lane, uint32_t* key, uint16_t* val,
+RT_D int resolve_keys(const float4* __restrict__ nrm0, const uint32_t* __restrict__ term, int spp, int lane, uint32_t* key, uint16_t* idx,
                       int* unordered) {
+  const unsigned lt = (1u << lane) - 1u;
   int n = 0, bad = 0;
-  uint32_t prev = 0;  // last key of the previous 32-chunk (lane 31), for the sortedness test
-  for (int base = 0; base < np; base += 32) {
+  uint32_t prev = 0;  // largest key so far (keys ascend as long as nothing is `bad`)
+  for (int base = 0; base < spp; base += 32) {
     const int i = base + lane;
     uint32_t k = 0xffffffffu;
     if (i < spp) {
@@ -1050,51 +1094,60 @@ RT_D int resolve_keys(const float4* __restrict__ nrm0, const uint32_t* __restric
         const uint32_t t = term[i];
         if (t >> 30) k = t & 0x3fffffffu;
       }
+      key[i] = k;
     }
-    key[i] = k;
-    val[i] = (uint16_t)i;
-    n += __popc(__ballot_sync(0xffffffffu, k != 0xffffffffu));
-    uint32_t pk = __shfl_up_sync(0xffffffffu, k, 1);
-    if (lane == 0) pk = prev;
-    bad |= (i > 0) && pk > k;
-    prev = __shfl_sync(0xffffffffu, k, 31);
+    const bool valid = k != 0xffffffffu;
+    const unsigned vm = __ballot_sync(0xffffffffu, valid);
+    if (valid) idx[n + __popc(vm & lt)] = (uint16_t)i;
+    // sortedness among the valid keys: compare with the previous valid key (of this chunk, else of earlier chunks)
+    const unsigned below = vm & lt;
+    const int pl = below ? 31 - __clz(below) : -1;
+    const uint32_t pk_in = __shfl_sync(0xffffffffu, k, pl < 0 ? 0 : pl);
+    const uint32_t pk = pl < 0 ? prev : pk_in;
+    bad |= valid && (n + __popc(below) > 0) && pk > k;
+    if (vm) prev = __shfl_sync(0xffffffffu, k, 31 - __clz(vm));
+    n += __popc(vm);
   }
   *unordered = __any_sync(0xffffffffu, bad);
   return n;
 }
-// Strictly sequential float sums over the first n entries of val[] (the reference's accumulation order), channel lanes
-// [0, n_lanes): lane l adds component l % 3 of src[val[i]] when the entry's class matches (`want` < 0: every entry).  The
-// payload of 32 entries at a time is gathered by the whole warp (32 loads in flight, the next chunk already requested),
-// staged in shared memory and then read back in order by the channel lanes: the sum itself stays one dependent FADD chain per
-// channel, its operands no longer arrive one L2 round trip at a time (round-2 finding: at 4096 spp the per-lane gathers made
-// this kernel 12 % of a frame).
-RT_D float resolve_sum(const float4* __restrict__ src, const uint32_t* __restrict__ term, const uint16_t* val, int n, int lane, int n_lanes,
-                       int want, float4* stage) {
+// Strictly sequential float sums over the n entries of order[] (the reference's accumulation order), channel lanes
+// [0, n_rows): row r of the staging buffer holds, for 32 entries at a time, the value lane r has to add - component r % 3 of
+// src[order[i]] if the entry's class matches the row's (`want_lo` for rows 0-2, `want_hi` for rows 3-5; < 0: every entry), else
+// +0.0f (an exact no-op: the accumulator can never be -0).  The payload is gathered by the whole warp (32 loads in flight, the
+// next chunk already requested), so the sum itself is one dependent FADD chain per channel fed from shared memory.
+RT_D float resolve_sum(const float4* __restrict__ src, const uint32_t* __restrict__ term, const uint16_t* order, int n, int lane, int n_rows,
+                       int want_lo, int want_hi, float* stage) {
   auto fetch = [&](int base) {
     float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     const int i = base + lane;
     if (i < n) {
-      const int p = val[i];
+      const int p = order[i];
       v = src[p];
       v.w = term ? __uint_as_float(term[p] >> 30) : 0.0f;
     }
     return v;
   };
-  const int ch = lane % 3;
   float acc = 0.0f;
   float4 cur = fetch(0);
   for (int base = 0; base < n; base += 32) {
     const float4 nxt = fetch(base + 32);
-    stage[lane] = cur;
+    const int kind = (int)__float_as_uint(cur.w);
+    const bool lo = want_lo < 0 || kind == want_lo, hi = want_hi < 0 || kind == want_hi;
+    stage[0 * RES_ROW + lane] = lo ? cur.x : 0.0f;
+    stage[1 * RES_ROW + lane] = lo ? cur.y : 0.0f;
+    stage[2 * RES_ROW + lane] = lo ? cur.z : 0.0f;
+    if (n_rows > 3) {
+      stage[3 * RES_ROW + lane] = hi ? cur.x : 0.0f;
+      stage[4 * RES_ROW + lane] = hi ? cur.y : 0.0f;
+      stage[5 * RES_ROW + lane] = hi ? cur.z : 0.0f;
+    }
     __syncwarp();
     const int m = min(32, n - base);
-    if (lane < n_lanes) {
+    if (lane < n_rows) {
+      const float* row = stage + lane * RES_ROW;
 #pragma unroll 8
-      for (int j = 0; j < m; ++j) {
-        const float4 e = stage[j];
-        const float x = ch == 0 ? e.x : (ch == 1 ? e.y : e.z);
-        acc += (want < 0 || (int)__float_as_uint(e.w) == want) ? x : 0.0f;
-      }
+      for (int j = 0; j < m; ++j) acc += row[j];
     }
     __syncwarp();
     cur = nxt;
@@ -1107,9 +1160,11 @@ __global__ void __launch_bounds__(RES_MAX_WARPS * 32) k_resolve(const DevFrame f
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* mine = smem_raw + (size_t)warp * resolve_smem_per_warp(np);
-  float4* stage = reinterpret_cast<float4*>(mine);
-  uint32_t* key = reinterpret_cast<uint32_t*>(stage + 32);
-  uint16_t* val = reinterpret_cast<uint16_t*>(key + np);
+  float* stage = reinterpret_cast<float*>(mine);
+  int* hist = reinterpret_cast<int*>(stage + RES_STAGE_FLOATS);
+  uint32_t* key = reinterpret_cast<uint32_t*>(hist + 256);
+  uint16_t* idx0 = reinterpret_cast<uint16_t*>(key + np);
+  uint16_t* idx1 = idx0 + np;
   const int ts = blockIdx.y, pl = blockIdx.x * wpc + warp;
   const TileGeom tg = tile_geom(fr, pb.tile_ids[ts]);
   if (pl >= tg.tw * tg.th) return;  // warp-uniform
@@ -1122,24 +1177,23 @@ __global__ void __launch_bounds__(RES_MAX_WARPS * 32) k_resolve(const DevFrame f
   const float div = (float)fr.spp;
   int unordered;
   // WorldNormal xyz (lanes 0-2) and Alpha in depth-0 slot order
-  const int nA = resolve_keys<0>(nrm0, term, fr.spp, np, lane, key, val, &unordered);
-  __syncwarp();
-  if (unordered) warp_bitonic(key, val, np, lane);
-  __syncwarp();
   {
-    const float acc = resolve_sum(nrm0, nullptr, val, nA, lane, 3, -1, stage);
+    const int nA = resolve_keys<0>(nrm0, term, fr.spp, lane, key, idx0, &unordered);
+    __syncwarp();
+    const uint16_t* order = unordered ? warp_radix_sort(key, idx0, idx1, nA, lane, hist) : idx0;
+    __syncwarp();
+    const float acc = resolve_sum(nrm0, nullptr, order, nA, lane, 3, -1, -1, stage);
     if (lane < 3 && normal) normal[3 * pix + lane] = acc / div;
     if (lane == 3 && alpha) alpha[pix] = (float)nA / div;  // Alpha(1.0) per depth-0 receives_light sample: a sum of nA ones is nA exactly
   }
   __syncwarp();
-  // Color rgb (lanes 0-2) and Background rgb (lanes 3-5) in (depth, slot) order.  (A Color lane adds +0.0f for a Background
-  // entry and vice versa: exact no-ops, the accumulator can never be -0.)
-  const int nB = resolve_keys<1>(nrm0, term, fr.spp, np, lane, key, val, &unordered);
-  __syncwarp();
-  if (unordered) warp_bitonic(key, val, np, lane);
-  __syncwarp();
+  // Color rgb (lanes 0-2) and Background rgb (lanes 3-5) in (depth, slot) order
   {
-    const float acc = resolve_sum(rad, term, val, nB, lane, 6, lane < 3 ? (int)TERM_COLOR : (int)TERM_BACKGROUND, stage);
+    const int nB = resolve_keys<1>(nrm0, term, fr.spp, lane, key, idx0, &unordered);
+    __syncwarp();
+    const uint16_t* order = unordered ? warp_radix_sort(key, idx0, idx1, nB, lane, hist) : idx0;
+    __syncwarp();
+    const float acc = resolve_sum(rad, term, order, nB, lane, 6, (int)TERM_COLOR, (int)TERM_BACKGROUND, stage);
     float* dst = lane < 3 ? color : background;
     if (lane < 6 && dst) dst[3 * pix + lane % 3] = acc / div;
   }
