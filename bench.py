@@ -495,8 +495,9 @@ def main():
             also["cfg2"] = {k: r2[k] for k in ("workload", "value", "unit", "ms_per_step", "steps", "warmup", "e2e", "gpu_launches", "roofline", "kernels") if k in r2}
             also["cfg2"]["note"] = "BASELINE config 2 (1 GPU): authored Mandelbulb, no rayn counterpart (SURVEY F1)"
         if args.config != 5:
-            r5 = b.run_config(5, "strong", 1, 1, breakdown=False, e2e=False)  # one untimed step first: pass buffers (25 GB) are allocated lazily
-            also["cfg5_strong"] = {k: r5[k] for k in ("workload", "value", "unit", "ms_per_step", "steps", "warmup", "gpu_launches", "parity", "passes_per_step", "scaling") if k in r5}
+            # one untimed step first: pass buffers (25 GB) are allocated lazily.  Per-kernel breakdown only at N > 1 (two more frames)
+            r5 = b.run_config(5, "strong", 1, 1, breakdown=world > 1, e2e=False)
+            also["cfg5_strong"] = {k: r5[k] for k in ("workload", "value", "unit", "ms_per_step", "steps", "warmup", "gpu_launches", "parity", "passes_per_step", "scaling", "kernels") if k in r5}
             also["cfg5_strong"]["note"] = ("BASELINE config 5 (7680x4320 Mandelbulb, 1024 spp, 8 bounces), the FIXED frame tiled across the N GPUs of this run: "
                                            "value(N) / value(1) over the driver's 1/2/4/8 runs is the strong-scaling curve; one timed step after one untimed step (a step is tens of seconds at N = 1)")
             if not r5.get("parity_ok", True):

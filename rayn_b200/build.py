@@ -34,7 +34,10 @@ VARIANTS = {  # file name -> extra defines
 }
 if os.environ.get("RAYN_BUILD_EXPERIMENTS"):  # tuning experiments only (selected with RAYN_B200_LIB=<file name>)
     for occ in os.environ["RAYN_BUILD_EXPERIMENTS"].split(","):
-        VARIANTS[f"librayn_b200_occ{occ}.so"] = ["-DRAYN_MULADD_FUSED=0", f"-DRAYN_MARCH_OCC={occ}"]
+        if occ.startswith("b"):  # "b6": only the Mandelbulb march kernels at 6 CTAs per SM
+            VARIANTS[f"librayn_b200_occ{occ}.so"] = ["-DRAYN_MULADD_FUSED=0", f"-DRAYN_MARCH_OCC_BULB={occ[1:]}"]
+        else:
+            VARIANTS[f"librayn_b200_occ{occ}.so"] = ["-DRAYN_MULADD_FUSED=0", f"-DRAYN_MARCH_OCC={occ}"]
 HOSTINPUTS = os.path.join(OUT_DIR, "librayn_hostinputs.so")
 
 

@@ -656,6 +656,9 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
   pb.seg_count = ctx->d_work_ctr + WC_SEG_COUNT;
   CU(cudaMemsetAsync(pb.counters, 0, CNT_TOTAL * sizeof(unsigned long long), st));
   const size_t res_smem = resolve_smem_per_warp(np) * wpc;
+  int slot_bits = 5, depth_bits = 1;  // significant bits of a shading slot (< QS) and of a depth (<= max_bounces): what k_resolve's radix sort walks
+  while ((1 << slot_bits) < QS + 1) ++slot_bits;
+  while ((1 << depth_bits) < mb + 1) ++depth_bits;
   CU(cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem));
 
   // Small single-pass frames are launch bound (config 1: ~20 launches of a few microseconds each): capture the whole kernel
@@ -791,7 +794,7 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
       }
     }
     timed_begin(ctx, RAYN_K_RESOLVE);
-    k_resolve<<<dim3((f->tile_w * f->tile_h + wpc - 1) / wpc, nt), wpc * 32, res_smem, st>>>(fr, pb, p_color, p_alpha, p_bg, p_normal, np, wpc);
+    k_resolve<<<dim3((f->tile_w * f->tile_h + wpc - 1) / wpc, nt), wpc * 32, res_smem, st>>>(fr, pb, p_color, p_alpha, p_bg, p_normal, np, wpc, slot_bits, depth_bits);
     timed_end(ctx, RAYN_K_RESOLVE);
     if (capturing) {
       cudaGraph_t graph = nullptr;

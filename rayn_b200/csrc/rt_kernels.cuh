@@ -381,8 +381,12 @@ __global__ void __launch_bounds__(256) k_extend_spheres(const __grid_constant__ 
 #ifndef RAYN_MARCH_OCC
 #define RAYN_MARCH_OCC 8  // resident CTAs per SM the march kernels are compiled for (register budget 65536 / (128 * OCC))
 #endif
+#ifndef RAYN_MARCH_OCC_BULB
+#define RAYN_MARCH_OCC_BULB RAYN_MARCH_OCC  // same for the authored Mandelbulb estimator (needs more registers; tuning hook)
+#endif
+#define MARCH_OCC(V) ((V) == SDFV_BULB ? RAYN_MARCH_OCC_BULB : RAYN_MARCH_OCC)
 template <int V>
-__global__ void __launch_bounds__(EXT_T, RAYN_MARCH_OCC) k_extend_march(const __grid_constant__ DevScene sc, const PassBufs pb, const Thr thr,
+__global__ void __launch_bounds__(EXT_T, MARCH_OCC(V)) k_extend_march(const __grid_constant__ DevScene sc, const PassBufs pb, const Thr thr,
                                                           const int hk, const int spheres_first, const int* __restrict__ batch_prefix,
                                                           int* __restrict__ work_ctr) {
   const SdfK k = make_sdfk(sc.hit[hk], sc.one);  // fractal constants: kernel-parameter bank -> registers, once
@@ -741,7 +745,7 @@ __global__ void __launch_bounds__(128, 8) k_shade_pre(const __grid_constant__ De
 #define SHD_T 128
 #define SHD_BATCH 128
 template <int V>
-__global__ void __launch_bounds__(SHD_T, RAYN_MARCH_OCC) k_shadow(const __grid_constant__ DevScene sc, const PassBufs pb, const int hk, const int j,
+__global__ void __launch_bounds__(SHD_T, MARCH_OCC(V)) k_shadow(const __grid_constant__ DevScene sc, const PassBufs pb, const int hk, const int j,
                                                     int* __restrict__ work_ctr) {
   const SdfK k = make_sdfk(sc.hit[hk], sc.one);
   const int lane = threadIdx.x & 31;
@@ -1006,37 +1010,42 @@ __global__ void __launch_bounds__(CMP_T) k_compact_scatter(const PassBufs pb, co
 // HBM; one warp per pixel puts 4-16x more pixels in flight per SM.)
 // ------------------------------------------------------------------------------------------
 #define RES_MAX_WARPS 8
+#define RES_BINS 512  // histogram bins of the radix sort (digits of up to 9 bits)
 #define RES_ROW 33                       // staging rows are 32 entries + 1 pad: the channel lanes read their rows bank-conflict free
 #define RES_STAGE_FLOATS (6 * RES_ROW + 2)  // staging buffer of the ordered sums: up to 6 channel rows
-// per warp: key[np] (by sample index), two index arrays (ping-pong of the radix sort), 256 histogram bins, the staging rows
+// per warp: key[np] (by sample index), two index arrays (ping-pong of the radix sort), the histogram bins, the staging rows
 __host__ __device__ inline size_t resolve_smem_per_warp(int np) {
-  return (size_t)np * (sizeof(uint32_t) + 2 * sizeof(uint16_t)) + 256 * sizeof(int) + RES_STAGE_FLOATS * sizeof(float);
+  return (size_t)np * (sizeof(uint32_t) + 2 * sizeof(uint16_t)) + RES_BINS * sizeof(int) + RES_STAGE_FLOATS * sizeof(float);
 }
 static inline int resolve_warps_per_cta(int np) {
   int w = (int)((size_t)200 * 1024 / resolve_smem_per_warp(np));
   return w < 1 ? 0 : (w > RES_MAX_WARPS ? RES_MAX_WARPS : w);
 }
-// One warp sorts the n sample indices in src[] by key[index] ascending: LSD radix sort, 8 bits per pass, stable, passes whose
-// digit is the same for every key are skipped.  Returns the array that holds the result (src or tmp).  (The bitonic network it
-// replaces needed 78 dependent shared-memory stages at 4096 spp - 400 k cycles per pixel at two warps per scheduler.)
-RT_D uint16_t* warp_radix_sort(const uint32_t* key, uint16_t* src, uint16_t* tmp, int n, int lane, int* hist) {
+// One warp sorts the n sample indices in src[] by key[index] ascending: LSD radix sort over the low key_bits bits, stable, in
+// ceil(key_bits / 9) passes of equal digit width (<= 9 bits), passes whose digit is the same for every key are skipped.
+// Returns the array that holds the result (src or tmp).  (The bitonic network it replaces needed 78 dependent shared-memory
+// stages at 4096 spp - 400 k cycles per pixel at two warps per scheduler.)
+RT_D uint16_t* warp_radix_sort(const uint32_t* key, uint16_t* src, uint16_t* tmp, int n, int key_bits, int lane, int* hist) {
   const unsigned lt = (1u << lane) - 1u;
-  for (int shift = 0; shift < 32; shift += 8) {
-    for (int b = lane; b < 256; b += 32) hist[b] = 0;
+  const int passes = (key_bits + 8) / 9, dbits = (key_bits + passes - 1) / passes;  // digit width <= 9
+  const unsigned dmask = (1u << dbits) - 1u;
+  const int per_lane = (1 << dbits) >> 5;  // bins owned by a lane in the scan (dbits >= 5 as long as key_bits >= 5)
+  for (int shift = 0; shift < key_bits; shift += dbits) {
+    for (int b = lane; b <= (int)dmask; b += 32) hist[b] = 0;
     __syncwarp();
+#pragma unroll 4
     for (int base = 0; base < n; base += 32) {
       const int i = base + lane;
-      if (i < n) atomicAdd(&hist[(key[src[i]] >> shift) & 255u], 1);
+      if (i < n) atomicAdd(&hist[(key[src[i]] >> shift) & dmask], 1);
     }
     __syncwarp();
-    // exclusive scan of the 256 bins: lane l owns bins 8l .. 8l+7
-    int c[8], sum = 0;
+    // exclusive scan of the bins: lane l owns bins per_lane * l .. per_lane * (l + 1) - 1
+    int sum = 0;
     bool uniform = false;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      c[q] = hist[8 * lane + q];
-      uniform |= c[q] == n;
-      sum += c[q];
+    for (int q = 0; q < per_lane; ++q) {
+      const int c = hist[per_lane * lane + q];
+      uniform |= c == n;
+      sum += c;
     }
     if (__any_sync(0xffffffffu, uniform)) continue;  // every key has the same digit here: nothing to do
     int incl = sum;
@@ -1045,17 +1054,17 @@ RT_D uint16_t* warp_radix_sort(const uint32_t* key, uint16_t* src, uint16_t* tmp
       if (lane >= o) incl += y;
     }
     int run = incl - sum;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      hist[8 * lane + q] = run;
-      run += c[q];
+    for (int q = 0; q < per_lane; ++q) {
+      const int c = hist[per_lane * lane + q];
+      hist[per_lane * lane + q] = run;
+      run += c;
     }
     __syncwarp();
     for (int base = 0; base < n; base += 32) {
       const int i = base + lane;
       const bool act = i < n;
       const int v = act ? src[i] : 0;
-      const unsigned d = act ? ((key[v] >> shift) & 255u) : (256u + lane);  // inactive lanes: singleton groups
+      const unsigned d = act ? ((key[v] >> shift) & dmask) : (RES_BINS + lane);  // inactive lanes: singleton groups
       const unsigned m = __match_any_sync(0xffffffffu, d);
       const int leader = __ffs(m) - 1;
       int pos = 0;
@@ -1076,10 +1085,11 @@ RT_D uint16_t* warp_radix_sort(const uint32_t* key, uint16_t* src, uint16_t* tmp
 // keys of one order into shared memory (key[sample index]) and the indices of the samples that take part, in sample order,
 // into idx[]; returns their number, *unordered != 0 if their keys are not ascending already.
 // WHICH = 0: depth-0 slot + 1 of receives_light hits (WorldNormal / Alpha order, integrator.rs:161-169);
-// WHICH = 1: (depth, slot) at termination (Color / Background order, integrator.rs:178-203).
+// WHICH = 1: (depth, slot) at termination (Color / Background order, integrator.rs:178-203), packed as depth << slot_bits | slot
+// (slot < 2^slot_bits) so that the radix sort sees as few significant bits as possible.
 template <int WHICH>
-RT_D int resolve_keys(const float4* __restrict__ nrm0, const uint32_t* __restrict__ term, int spp, int lane, uint32_t* key, uint16_t* idx,
-                      int* unordered) {
+RT_D int resolve_keys(const float4* __restrict__ nrm0, const uint32_t* __restrict__ term, const float4* __restrict__ prefetch, int spp, int slot_bits,
+                      int lane, uint32_t* key, uint16_t* idx, int* unordered) {
   const unsigned lt = (1u << lane) - 1u;
   int n = 0, bad = 0;
   uint32_t prev = 0;  // largest key so far (keys ascend as long as nothing is `bad`)
@@ -1092,7 +1102,8 @@ RT_D int resolve_keys(const float4* __restrict__ nrm0, const uint32_t* __restric
         if (s0) k = s0;
       } else {
         const uint32_t t = term[i];
-        if (t >> 30) k = t & 0x3fffffffu;
+        if (t >> 30) k = (((t >> TERM_DEPTH_SHIFT) & 0xffu) << slot_bits) | (t & (TERM_MAX_SLOTS - 1u));  // same order, fewer significant bits
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(prefetch + i));  // the payload the ordered sum will gather (same pixel, permuted order)
       }
       key[i] = k;
     }
@@ -1129,9 +1140,9 @@ RT_D float resolve_sum(const float4* __restrict__ src, const uint32_t* __restric
     return v;
   };
   float acc = 0.0f;
-  float4 cur = fetch(0);
+  float4 cur = fetch(0), nxt = fetch(32);
   for (int base = 0; base < n; base += 32) {
-    const float4 nxt = fetch(base + 32);
+    const float4 nxt2 = fetch(base + 64);  // two chunks in flight ahead of the one being summed
     const int kind = (int)__float_as_uint(cur.w);
     const bool lo = want_lo < 0 || kind == want_lo, hi = want_hi < 0 || kind == want_hi;
     stage[0 * RES_ROW + lane] = lo ? cur.x : 0.0f;
@@ -1151,18 +1162,20 @@ RT_D float resolve_sum(const float4* __restrict__ src, const uint32_t* __restric
     }
     __syncwarp();
     cur = nxt;
+    nxt = nxt2;
   }
   return acc;
 }
 __global__ void __launch_bounds__(RES_MAX_WARPS * 32) k_resolve(const DevFrame fr, const PassBufs pb, float* __restrict__ color,
                                                                  float* __restrict__ alpha, float* __restrict__ background,
-                                                                 float* __restrict__ normal, const int np, const int wpc) {
+                                                                 float* __restrict__ normal, const int np, const int wpc, const int slot_bits,
+                                                                 const int depth_bits) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned char* mine = smem_raw + (size_t)warp * resolve_smem_per_warp(np);
   float* stage = reinterpret_cast<float*>(mine);
   int* hist = reinterpret_cast<int*>(stage + RES_STAGE_FLOATS);
-  uint32_t* key = reinterpret_cast<uint32_t*>(hist + 256);
+  uint32_t* key = reinterpret_cast<uint32_t*>(hist + RES_BINS);
   uint16_t* idx0 = reinterpret_cast<uint16_t*>(key + np);
   uint16_t* idx1 = idx0 + np;
   const int ts = blockIdx.y, pl = blockIdx.x * wpc + warp;
@@ -1178,9 +1191,9 @@ __global__ void __launch_bounds__(RES_MAX_WARPS * 32) k_resolve(const DevFrame f
   int unordered;
   // WorldNormal xyz (lanes 0-2) and Alpha in depth-0 slot order
   {
-    const int nA = resolve_keys<0>(nrm0, term, fr.spp, lane, key, idx0, &unordered);
+    const int nA = resolve_keys<0>(nrm0, term, nrm0, fr.spp, slot_bits, lane, key, idx0, &unordered);
     __syncwarp();
-    const uint16_t* order = unordered ? warp_radix_sort(key, idx0, idx1, nA, lane, hist) : idx0;
+    const uint16_t* order = unordered ? warp_radix_sort(key, idx0, idx1, nA, slot_bits + 1, lane, hist) : idx0;
     __syncwarp();
     const float acc = resolve_sum(nrm0, nullptr, order, nA, lane, 3, -1, -1, stage);
     if (lane < 3 && normal) normal[3 * pix + lane] = acc / div;
@@ -1189,9 +1202,9 @@ __global__ void __launch_bounds__(RES_MAX_WARPS * 32) k_resolve(const DevFrame f
   __syncwarp();
   // Color rgb (lanes 0-2) and Background rgb (lanes 3-5) in (depth, slot) order
   {
-    const int nB = resolve_keys<1>(nrm0, term, fr.spp, lane, key, idx0, &unordered);
+    const int nB = resolve_keys<1>(nrm0, term, rad, fr.spp, slot_bits, lane, key, idx0, &unordered);
     __syncwarp();
-    const uint16_t* order = unordered ? warp_radix_sort(key, idx0, idx1, nB, lane, hist) : idx0;
+    const uint16_t* order = unordered ? warp_radix_sort(key, idx0, idx1, nB, slot_bits + depth_bits, lane, hist) : idx0;
     __syncwarp();
     const float acc = resolve_sum(rad, term, order, nB, lane, 6, (int)TERM_COLOR, (int)TERM_BACKGROUND, stage);
     float* dst = lane < 3 ? color : background;
