@@ -34,7 +34,9 @@ VARIANTS = {  # file name -> extra defines
 }
 if os.environ.get("RAYN_BUILD_EXPERIMENTS"):  # tuning experiments only (selected with RAYN_B200_LIB=<file name>)
     for occ in os.environ["RAYN_BUILD_EXPERIMENTS"].split(","):
-        if occ.startswith("b"):  # "b6": only the Mandelbulb march kernels at 6 CTAs per SM
+        if occ.startswith("p"):  # "p7": k_shade_pre at 7 CTAs per SM
+            VARIANTS[f"librayn_b200_occ{occ}.so"] = ["-DRAYN_MULADD_FUSED=0", f"-DRAYN_SHADE_PRE_OCC={occ[1:]}"]
+        elif occ.startswith("b"):  # "b6": only the Mandelbulb march kernels at 6 CTAs per SM
             VARIANTS[f"librayn_b200_occ{occ}.so"] = ["-DRAYN_MULADD_FUSED=0", f"-DRAYN_MARCH_OCC_BULB={occ[1:]}"]
         else:
             VARIANTS[f"librayn_b200_occ{occ}.so"] = ["-DRAYN_MULADD_FUSED=0", f"-DRAYN_MARCH_OCC={occ}"]

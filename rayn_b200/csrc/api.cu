@@ -73,7 +73,8 @@ struct RaynContext {
   int* d_batch_prefix = nullptr;  // [alloc_tiles + 1]
   int* d_work_ctr = nullptr;      // [WC_TOTAL] global work counters of the persistent kernels
   int n_sm = 148;
-  int occ_ext[SDFV_COUNT], occ_shd[SDFV_COUNT];
+  int occ_ext[SDFV_COUNT], occ_shd[SDFV_COUNT], occ_nrm[SDFV_COUNT];
+  int occ_pre = 8, occ_post = 8, occ_sph = 8;  // resident CTAs per SM of the work-list kernels
   int sdf_var[RAYN_MAX_HITABLES];  // march-kernel variant of every SDF hitable of the uploaded scene (rt_sdf2.cuh::sdf_variant)
   struct Div3Check { float min_r2, fixed_r2; bool ok; };
   std::vector<Div3Check> div3_cache;  // exhaustive fastdiv2_3 checks already run on this device
@@ -157,7 +158,7 @@ static void free_pass(RaynContext* c) {
   cudaFree(c->d_tile_ids);
   cudaFree(c->d_batch_prefix);
   c->d_batch_prefix = nullptr;
-  cudaFree(p.nrm), cudaFree(p.vis), cudaFree(p.seg_a), cudaFree(p.seg_b), cudaFree(p.lc_c), cudaFree(p.lc_t), cudaFree(p.seg_cnt);
+  cudaFree(p.nrm), cudaFree(p.vis), cudaFree(p.seg_a), cudaFree(p.seg_b), cudaFree(p.lc_c), cudaFree(p.lc_t), cudaFree(p.seg_cnt), cudaFree(p.slot_prefix);
   unsigned long long* counters = p.counters;
   memset(&p, 0, sizeof p);
   p.counters = counters;
@@ -210,6 +211,8 @@ static int32_t ensure_pass(RaynContext* ctx, int n_tiles, int R, int QS, int seg
   PASS_ALLOC(ctx->d_tile_ids, n_tiles * sizeof(int));
   PASS_ALLOC(ctx->d_batch_prefix, ((size_t)n_tiles + 1) * sizeof(int));
   PASS_ALLOC(p.seg_cnt, need_segcnt * sizeof(int));
+  PASS_ALLOC(p.slot_prefix, (size_t)(1 + RAYN_MAX_HITABLES) * ((size_t)n_tiles + 1) * sizeof(int));
+  p.prefix_stride = n_tiles + 1;
   ctx->alloc_segcnt = need_segcnt;
   PASS_ALLOC(p.nrm, need_paths * sizeof(float4));
   PASS_ALLOC(p.vis, need_paths * sizeof(uint32_t));
@@ -343,8 +346,12 @@ int32_t rayn_b200_create(const RaynConfig* cfg, RaynContext** out_ctx) {
   // persistent kernels: exactly as many CTAs as can be resident (one wave), so every CTA pulls work until the pass is drained
   for (int v = 0; v < SDFV_COUNT && e == cudaSuccess; ++v) {
     DISPATCH_SDFV(v, e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_ext[v], k_extend_march<V>, EXT_T, 0);
-                  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shd[v], k_shadow<V>, SHD_T, 0));
+                  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_shd[v], k_shadow<V>, SHD_T, 0);
+                  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_nrm[v], k_normals<V>, SLOT_BLOCK, 0));
   }
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_pre, k_shade_pre, SLOT_BLOCK, 0);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_post, k_shade_post, SLOT_BLOCK, 0);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->occ_sph, k_extend_spheres, EXT_BATCH, 0);
   if (e != cudaSuccess) {
     cudaGetLastError();
     fail(nullptr, RAYN_ERR_CUDA, "context setup: %s", cudaGetErrorString(e));
@@ -698,6 +705,9 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
     }
     ctx->stats.passes++;
     const dim3 g_paths((R + 255) / 256, nt), g_shade((QS + 127) / 128, nt);
+    // resident grids (one wave) of the kernels that stride over a work list (k_scan_slots / k_scan_live), capped by the list's upper bound
+    const int64_t max_blocks = (int64_t)nt * ((QS + SLOT_BLOCK - 1) / SLOT_BLOCK);
+    auto resident = [&](int occ) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>((int64_t)ctx->n_sm * occ, max_blocks)); };
     const int nseg = (QS + SEG_SLOTS - 1) / SEG_SLOTS;  // segments per tile of the queue kernels
     timed_begin(ctx, RAYN_K_RAYGEN);
     k_raygen<<<g_paths, 256, 0, st>>>(ctx->scene, fr, pb, n_fold);
@@ -722,7 +732,7 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
           while (e < n_hit && ctx->scene.hit[e].kind == RAYN_HITABLE_SPHERE) ++e;
           if ((e > k || first_kernel) && !fold_all) {
             timed_begin(ctx, RAYN_K_EXTEND_SPHERES);
-            k_extend_spheres<<<g_paths, 256, 0, st>>>(ctx->scene, pb, k, e, first_kernel, motion ? 1 : 0);
+            k_extend_spheres<<<resident(ctx->occ_sph), EXT_BATCH, 0, st>>>(ctx->scene, pb, k, e, first_kernel, motion ? 1 : 0, ctx->d_batch_prefix, ctx->d_work_ctr + WC_SPHERES + k);
             timed_end(ctx, RAYN_K_EXTEND_SPHERES);
             first_kernel = 0;
           }
@@ -740,7 +750,8 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
       timed_begin(ctx, RAYN_K_BIN);
       k_bin_count<<<dim3(nseg, nt), BIN_T, 0, st>>>(pb, n_hit, nseg);
       k_bin_scatter<<<dim3(nseg, nt), BIN_T, 0, st>>>(pb, n_hit, nseg);
-      timed_end(ctx, RAYN_K_BIN, 2);
+      if (!simple) k_scan_slots<<<1, SCAN_T, 0, st>>>(ctx->scene, pb);  // work lists of k_normals / k_shade_pre / k_shade_post
+      timed_end(ctx, RAYN_K_BIN, simple ? 2 : 3);
       if (ctx->qlog_enabled) {
         h_nslots.resize(nt);
         h_slots.resize((size_t)nt * QS);
@@ -762,11 +773,11 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
           if (!(mk == RAYN_MATERIAL_LAMBERTIAN || mk == RAYN_MATERIAL_DIELECTRIC || volume_on)) continue;
           const int v = ctx->sdf_var[sdf_idx[j]];
           timed_begin(ctx, RAYN_K_NORMALS);
-          DISPATCH_SDFV(v, (k_normals<V><<<g_shade, 128, 0, st>>>(ctx->scene, pb, thr, sdf_idx[j])));
+          DISPATCH_SDFV(v, (k_normals<V><<<resident(ctx->occ_nrm[v]), SLOT_BLOCK, 0, st>>>(ctx->scene, pb, thr, sdf_idx[j], j, ctx->d_work_ctr + WC_NORMALS + j)));
           timed_end(ctx, RAYN_K_NORMALS);
         }
         timed_begin(ctx, RAYN_K_SHADE_PRE);
-        k_shade_pre<<<g_shade, 128, 0, st>>>(ctx->scene, fr, pb, depth, thr);
+        k_shade_pre<<<resident(ctx->occ_pre), SLOT_BLOCK, 0, st>>>(ctx->scene, fr, pb, depth, thr, ctx->d_work_ctr + WC_PRE);
         timed_end(ctx, RAYN_K_SHADE_PRE);
         if (ctx->scene.n_lights > 0) {
           for (int j = 0; j < n_sdf; ++j) {
@@ -777,7 +788,7 @@ static int32_t render_enqueue(RaynContext* ctx, const RaynFrameDesc* f, const Ra
           }
         }
         timed_begin(ctx, RAYN_K_SHADE_POST);
-        k_shade_post<<<g_shade, 128, 0, st>>>(ctx->scene, fr, pb, depth, n_fold);
+        k_shade_post<<<resident(ctx->occ_post), SLOT_BLOCK, 0, st>>>(ctx->scene, fr, pb, depth, n_fold, ctx->d_work_ctr + WC_POST);
         timed_end(ctx, RAYN_K_SHADE_POST);
       } else {
 #ifdef RAYN_LEGACY_KERNELS

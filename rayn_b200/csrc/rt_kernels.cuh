@@ -70,13 +70,19 @@ struct PassBufs {
   float* lc_t;        // [paths * 8] volume rounds only: transmission to the scatter point (integrator.rs:122-126)
   int lc_ns;          // light samples per path per depth: 4, or 4 * (1 + vm) with volumetrics
   int* seg_cnt;       // [n_tiles * nseg * RAYN_MAX_HITABLES] scratch of the segmented queue kernels (k_bin_*, k_compact_*)
+  // work lists of the slot-parallel kernels (k_scan_slots): row 0 = 128-slot blocks of every tile's shading queue, row 1 + j =
+  // 128-slot blocks of the bin of SDF ordinal j; each row is an exclusive prefix over the tiles with the total at [n_tiles]
+  int* slot_prefix;   // [(1 + RAYN_MAX_HITABLES) * prefix_stride]
+  int prefix_stride;  // >= n_tiles + 1
 };
 
 enum { CNT_EXTEND_RAYS = 0, CNT_SHADE_LANES = 1, CNT_SHADOW_RAYS = 2, CNT_EVALS_EXTEND = 3, CNT_EVALS_SHADOW = 4,
        CNT_BULB_ITERS_EXTEND = 5, CNT_BULB_ITERS_SHADOW = 6, CNT_EVALS_NORMALS = 7, CNT_TRIPS_EXTEND = 8, CNT_TRIPS_SHADOW = 9, CNT_TOTAL = 10 };  // Mandelbulb iterations actually run (the count is data dependent)
 
 // global work counters of the persistent kernels (RaynContext::d_work_ctr), zeroed by k_scan_live every depth
-enum { WC_EXTEND = 0, WC_SHADOW = 1 /* + SDF ordinal */, WC_SEG_COUNT = 1 + RAYN_MAX_HITABLES /* + SDF ordinal */, WC_TOTAL = 1 + 2 * RAYN_MAX_HITABLES };
+enum { WC_EXTEND = 0, WC_SHADOW = 1 /* + SDF ordinal */, WC_SEG_COUNT = 1 + RAYN_MAX_HITABLES /* + SDF ordinal */,
+       WC_PRE = 1 + 2 * RAYN_MAX_HITABLES, WC_POST = WC_PRE + 1, WC_NORMALS = WC_POST + 1 /* + SDF ordinal */,
+       WC_SPHERES = WC_NORMALS + RAYN_MAX_HITABLES /* + first hitable of the run */, WC_TOTAL = WC_SPHERES + RAYN_MAX_HITABLES };
 
 #define TERM_NONE 0u
 #define TERM_COLOR 1u
@@ -318,38 +324,129 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_live(const PassBufs pb, int* __
   if (tid == 0) batch_prefix[pb.n_tiles] = carry;
 }
 
+// Work lists of the slot-parallel kernels.  Round-2 launch list (profiles/r02_cfg3_launches.md): with a grid of
+// (QS / 128, tiles) blocks k_normals / k_shade_pre / k_shade_post cost a constant 0.41 ms per launch at depths 4-8, where hardly
+// a path is alive - 787 k empty blocks each, 5 % of a config-3 frame.  k_scan_slots (one CTA, after k_bin_scatter) lays the
+// NON-EMPTY 128-slot blocks of all tiles end to end; the kernels run a resident grid that strides over that list.
+#define SLOT_BLOCK 128
+__global__ void __launch_bounds__(SCAN_T) k_scan_slots(const __grid_constant__ DevScene sc, const PassBufs pb) {
+  __shared__ int wsum[SCAN_T / 32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int row = 0; row <= sc.n_sdf; ++row) {
+    int* __restrict__ out = pb.slot_prefix + (size_t)row * pb.prefix_stride;
+    const int hk = row ? sc.sdf_idx[row - 1] : 0;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < pb.n_tiles; base += SCAN_T) {
+      const int i = base + tid;
+      int v = 0;
+      if (i < pb.n_tiles) {
+        const int* __restrict__ bs = pb.bin_start + i * (RAYN_MAX_HITABLES + 1);
+        const int slots = row ? bs[hk + 1] - bs[hk] : pb.n_slots[i];
+        v = (slots + SLOT_BLOCK - 1) / SLOT_BLOCK;
+      }
+      int x = v;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      if (lane == 31) wsum[warp] = x;
+      __syncthreads();
+      if (warp == 0) {
+        int w = wsum[lane];
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(0xffffffffu, w, o);
+          if (lane >= o) w += y;
+        }
+        wsum[lane] = w;
+      }
+      __syncthreads();
+      const int excl = carry + (warp ? wsum[warp - 1] : 0) + x - v;
+      if (i < pb.n_tiles) out[i] = excl;
+      __syncthreads();
+      if (tid == SCAN_T - 1) carry = excl + v;
+      __syncthreads();
+    }
+    if (tid == 0) out[pb.n_tiles] = carry;
+    __syncthreads();
+  }
+}
+// The resident CTAs of a work-list kernel pull WORK_CHUNK consecutive 128-slot blocks at a time from a global counter (zeroed
+// by k_scan_live at the start of the depth).  Static striding was measured first: blocks differ 15x in cost (sky vs lit), the
+// slowest CTA ran ~10 % over the mean and k_shade_pre lost more than the empty blocks had cost.
+#define WORK_CHUNK 8
+RT_D int grab_chunk(int* __restrict__ ctr, int* s_slot) {
+  if (threadIdx.x == 0) *s_slot = atomicAdd(ctr, WORK_CHUNK);
+  __syncthreads();
+  const int c = *s_slot;
+  __syncthreads();
+  return c;
+}
+// work block wb of a prefix row -> tile slot whose blocks are [prefix[ts], prefix[ts + 1]) (every thread of the CTA runs the
+// same search; the loads broadcast from L1)
+RT_D int find_tile(const int* __restrict__ prefix, int n_tiles, int wb) {
+  int lo = 0, hi = n_tiles;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(prefix + mid) <= wb) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+// for (every work block wb of this CTA) BODY(ts, local)   with local = index of the block inside tile slot ts
+#define FOR_EACH_WORK_BLOCK(prefix, n_tiles, ctr, ...)                                  \
+  {                                                                                     \
+    __shared__ int s_chunk_;                                                            \
+    const int total_ = (prefix)[n_tiles];                                               \
+    for (;;) {                                                                          \
+      const int c0_ = grab_chunk(ctr, &s_chunk_);                                       \
+      if (c0_ >= total_) break;                                                         \
+      const int c1_ = min(c0_ + WORK_CHUNK, total_);                                    \
+      int ts = 0, begin_ = 0, end_ = 0;                                                 \
+      for (int wb_ = c0_; wb_ < c1_; ++wb_) {                                           \
+        if (wb_ >= end_) {                                                              \
+          ts = find_tile(prefix, n_tiles, wb_);                                         \
+          begin_ = __ldg((prefix) + ts), end_ = __ldg((prefix) + ts + 1);               \
+        }                                                                               \
+        const int local = wb_ - begin_;                                                 \
+        __VA_ARGS__                                                                     \
+      }                                                                                 \
+    }                                                                                   \
+  }
+
 // ---- K2 v4: closest hit split by hitable kind.  ncu on k_extend3 (profiles/r01 notes): the
 // per-ray prologue/epilogue (sphere tests, gathers, stores) ran at 1-4 active lanes inside the
 // persistent loop and cost more issue slots than the marches of cheap (sky) rays.  v4 keeps the
 // fold order of hitable.rs:177-198 but runs every maximal run of analytic spheres as a coherent
 // one-thread-per-ray kernel and every SDF hitable as a pure persistent march kernel.
-__global__ void __launch_bounds__(256) k_extend_spheres(const __grid_constant__ DevScene sc, const PassBufs pb, const int first,
-                                                        const int last, const int init, const int moving) {
-  const int ts = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int n = pb.n_live[ts];
-  if ((i & ~31) >= n) return;  // warp-uniform
-  const bool act = i < n;
-  if (act) {
-    const size_t q = (size_t)ts * pb.R + i;
-    const size_t g = (size_t)ts * pb.R + pb.q_live[q];
-    const float4 o4 = pb.o_time[g], d4 = pb.d_t[g];
-    const f3 o = mk3(o4.x, o4.y, o4.z), d = mk3(d4.x, d4.y, d4.z);
-    float closest = init ? sc.rc.world_radius * 2.0f : d4.w;  // film.rs:556
-    int id = init ? -1 : pb.q_key[g];
-    // packets of the extend stage are 4 consecutive live rays (film.rs:612-624); a moving sphere is evaluated at lane 0's time
-    float time0 = o4.w;
-    if (moving && (i & 3)) time0 = pb.o_time[(size_t)ts * pb.R + pb.q_live[(size_t)ts * pb.R + (i & ~3)]].w;
-    for (int k = first; k < last; ++k) {
-      const float t = moving ? sphere_hit(sc.hit[k], o, d, closest, time0) : sphere_hit_static(sc.sph[sc.hit_ord[k]], o, d, closest);
-      if (t < closest) {
-        closest = t;
-        id = k;
+__global__ void __launch_bounds__(EXT_BATCH) k_extend_spheres(const __grid_constant__ DevScene sc, const PassBufs pb, const int first, const int last,
+                                                              const int init, const int moving, const int* __restrict__ batch_prefix,
+                                                              int* __restrict__ work_ctr) {
+  // the 128-ray batches of k_scan_live: no block is launched for rays that are gone
+  FOR_EACH_WORK_BLOCK(batch_prefix, pb.n_tiles, work_ctr, {
+    const int i = local * EXT_BATCH + threadIdx.x;
+    const int n = pb.n_live[ts];
+    if (i < n) {
+      const size_t q = (size_t)ts * pb.R + i;
+      const size_t g = (size_t)ts * pb.R + pb.q_live[q];
+      const float4 o4 = pb.o_time[g], d4 = pb.d_t[g];
+      const f3 o = mk3(o4.x, o4.y, o4.z), d = mk3(d4.x, d4.y, d4.z);
+      float closest = init ? sc.rc.world_radius * 2.0f : d4.w;  // film.rs:556
+      int id = init ? -1 : pb.q_key[g];
+      // packets of the extend stage are 4 consecutive live rays (film.rs:612-624); a moving sphere is evaluated at lane 0's time
+      float time0 = o4.w;
+      if (moving && (i & 3)) time0 = pb.o_time[(size_t)ts * pb.R + pb.q_live[(size_t)ts * pb.R + (i & ~3)]].w;
+      for (int k = first; k < last; ++k) {
+        const float t = moving ? sphere_hit(sc.hit[k], o, d, closest, time0) : sphere_hit_static(sc.sph[sc.hit_ord[k]], o, d, closest);
+        if (t < closest) {
+          closest = t;
+          id = k;
+        }
       }
+      pb.d_t[g].w = closest;
+      pb.q_key[g] = id;
     }
-    pb.d_t[g].w = closest;
-    pb.q_key[g] = id;
-  }
+  })
 }
 
 // ------------------------------------------------------------------------------------------
@@ -519,31 +616,35 @@ __global__ void __launch_bounds__(EXT_T, MARCH_OCC(V)) k_extend_march(const __gr
 // per lane, specialised on the SDF like the march kernels.  Writes nrm[g] = (normal, offset_by).
 // ------------------------------------------------------------------------------------------
 template <int V>
-__global__ void __launch_bounds__(128, 8) k_normals(const __grid_constant__ DevScene sc, const PassBufs pb, const Thr thr, const int hk) {
-  const int ts = blockIdx.y;
-  const int* __restrict__ bs = pb.bin_start + ts * (RAYN_MAX_HITABLES + 1);
-  const int s0 = bs[hk], s1 = bs[hk + 1];
-  const int s = s0 + blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= s1) return;
-  const int id = pb.q_shade[(size_t)ts * pb.QS + s];
-  if (id < 0) return;  // padding lane (hitable.rs:100-111)
+__global__ void __launch_bounds__(128, 8) k_normals(const __grid_constant__ DevScene sc, const PassBufs pb, const Thr thr, const int hk, const int j,
+                                                    int* __restrict__ work_ctr) {
+  const int* __restrict__ prefix = pb.slot_prefix + (size_t)(1 + j) * pb.prefix_stride;  // 128-slot blocks of this SDF's bins, all tiles
   const SdfK k = make_sdfk(sc.hit[hk], sc.one);
-  const size_t g = (size_t)ts * pb.R + id;
-  const float4 o4 = pb.o_time[g], d4 = pb.d_t[g];
-  const f3 point = fma3s(mk3(d4.x, d4.y, d4.z), d4.w, mk3(o4.x, o4.y, o4.z));  // WHit::point -> ray.point_at, ray.rs:22-24
-  const float eps = dm::max(0.0001f, sc.rc.sdf_detail_scale * thr.at(d4.w));
-  // tetrahedron offsets k0 = (1,-1,-1), k1 = (-1,-1,1), k2 = (-1,1,-1), k3 = (1,1,1); n = ((k0 d0 + k1 d1) + k2 d2) + k3 d3
-  int it = 0;
-  const float ex = 1.0f * eps, en = -1.0f * eps;
-  const float2 da = sdf_dist2<V>(k, f2(point.x + ex, point.x + en), f2(point.y + en, point.y + en), f2(point.z + en, point.z + ex), it);
-  const float2 db = sdf_dist2<V>(k, f2(point.x + en, point.x + ex), f2(point.y + ex, point.y + ex), f2(point.z + en, point.z + ex), it);
-  f3 n = mk3(1.0f, -1.0f, -1.0f) * da.x;
-  n = n + mk3(-1.0f, -1.0f, 1.0f) * da.y;
-  n = n + mk3(-1.0f, 1.0f, -1.0f) * db.x;
-  n = n + mk3(1.0f, 1.0f, 1.0f) * db.y;
-  n = normalized(n);
-  pb.nrm[g] = make_float4(n.x, n.y, n.z, eps);
-  warp_add_partial(pb.counters + CNT_EVALS_NORMALS, 4);
+  int evals = 0;
+  FOR_EACH_WORK_BLOCK(prefix, pb.n_tiles, work_ctr, {
+    const int* __restrict__ bs = pb.bin_start + ts * (RAYN_MAX_HITABLES + 1);
+    const int s = bs[hk] + local * SLOT_BLOCK + threadIdx.x;
+    const int id = s < bs[hk + 1] ? pb.q_shade[(size_t)ts * pb.QS + s] : -1;
+    if (id >= 0) {  // < 0: beyond the bin, or a padding lane (hitable.rs:100-111)
+      const size_t g = (size_t)ts * pb.R + id;
+      const float4 o4 = pb.o_time[g], d4 = pb.d_t[g];
+      const f3 point = fma3s(mk3(d4.x, d4.y, d4.z), d4.w, mk3(o4.x, o4.y, o4.z));  // WHit::point -> ray.point_at, ray.rs:22-24
+      const float eps = dm::max(0.0001f, sc.rc.sdf_detail_scale * thr.at(d4.w));
+      // tetrahedron offsets k0 = (1,-1,-1), k1 = (-1,-1,1), k2 = (-1,1,-1), k3 = (1,1,1); n = ((k0 d0 + k1 d1) + k2 d2) + k3 d3
+      int it = 0;
+      const float ex = 1.0f * eps, en = -1.0f * eps;
+      const float2 da = sdf_dist2<V>(k, f2(point.x + ex, point.x + en), f2(point.y + en, point.y + en), f2(point.z + en, point.z + ex), it);
+      const float2 db = sdf_dist2<V>(k, f2(point.x + en, point.x + ex), f2(point.y + ex, point.y + ex), f2(point.z + en, point.z + ex), it);
+      f3 n = mk3(1.0f, -1.0f, -1.0f) * da.x;
+      n = n + mk3(-1.0f, -1.0f, 1.0f) * da.y;
+      n = n + mk3(-1.0f, 1.0f, -1.0f) * db.x;
+      n = n + mk3(1.0f, 1.0f, 1.0f) * db.y;
+      n = normalized(n);
+      pb.nrm[g] = make_float4(n.x, n.y, n.z, eps);
+      evals += 4;
+    }
+  })
+  warp_add(pb.counters + CNT_EVALS_NORMALS, evals);
 }
 // ==========================================================================================
 // v3 shading: k_shade_pre -> k_shadow (persistent) -> k_shade_post.
@@ -637,10 +738,7 @@ RT_D SlotCtx slot_ctx(const DevScene& sc, const DevFrame& fr, const PassBufs& pb
   return c;
 }
 
-__global__ void __launch_bounds__(128, 8) k_shade_pre(const __grid_constant__ DevScene sc, const DevFrame fr, const PassBufs pb,
-                                                      const int depth, const Thr thr) {
-  const int ts = blockIdx.y;
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+RT_D void shade_pre_slot(const DevScene& sc, const DevFrame& fr, const PassBufs& pb, const int depth, const Thr thr, const int ts, const int s) {
   const int nslots = pb.n_slots[ts];
   if ((s & ~31) >= nslots) return;  // warp-uniform
   const SlotCtx cx = slot_ctx(sc, fr, pb, ts, s, nslots, depth, threadIdx.x & 31);
@@ -734,6 +832,15 @@ __global__ void __launch_bounds__(128, 8) k_shade_pre(const __grid_constant__ De
     }
   }
   warp_add(pb.counters + CNT_SHADOW_RAYS, shadows);
+}
+
+#ifndef RAYN_SHADE_PRE_OCC
+#define RAYN_SHADE_PRE_OCC 8  // resident CTAs per SM k_shade_pre is compiled for (tuning hook)
+#endif
+__global__ void __launch_bounds__(128, RAYN_SHADE_PRE_OCC) k_shade_pre(const __grid_constant__ DevScene sc, const DevFrame fr, const PassBufs pb,
+                                                      const int depth, const Thr thr, int* __restrict__ work_ctr) {
+  // row 0 of the work lists: the non-empty 128-slot blocks of every tile's shading queue
+  FOR_EACH_WORK_BLOCK(pb.slot_prefix, pb.n_tiles, work_ctr, { shade_pre_slot(sc, fr, pb, depth, thr, ts, local * SLOT_BLOCK + threadIdx.x); })
 }
 
 // ------------------------------------------------------------------------------------------
@@ -851,10 +958,7 @@ __global__ void __launch_bounds__(SHD_T, MARCH_OCC(V)) k_shadow(const __grid_con
   if (V == SDFV_BULB) warp_add(pb.counters + CNT_BULB_ITERS_SHADOW, bulb_iters);
 }
 
-__global__ void __launch_bounds__(128, 8) k_shade_post(const __grid_constant__ DevScene sc, const DevFrame fr, const PassBufs pb,
-                                                       const int depth, const int pre_n) {
-  const int ts = blockIdx.y;
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+RT_D void shade_post_slot(const DevScene& sc, const DevFrame& fr, const PassBufs& pb, const int depth, const int pre_n, const int ts, const int s) {
   const int nslots = pb.n_slots[ts];
   if ((s & ~31) >= nslots) return;
   const SlotCtx cx = slot_ctx(sc, fr, pb, ts, s, nslots, depth, threadIdx.x & 31);
@@ -937,6 +1041,11 @@ __global__ void __launch_bounds__(128, 8) k_shade_post(const __grid_constant__ D
     pb.term[g] = ((depth == 0 ? TERM_BACKGROUND : TERM_COLOR) << 30) | ((unsigned)depth << TERM_DEPTH_SHIFT) | (unsigned)s;
     qs[s] = -1;
   }
+}
+
+__global__ void __launch_bounds__(128, 8) k_shade_post(const __grid_constant__ DevScene sc, const DevFrame fr, const PassBufs pb,
+                                                       const int depth, const int pre_n, int* __restrict__ work_ctr) {
+  FOR_EACH_WORK_BLOCK(pb.slot_prefix, pb.n_tiles, work_ctr, { shade_post_slot(sc, fr, pb, depth, pre_n, ts, local * SLOT_BLOCK + threadIdx.x); })
 }
 
 // ------------------------------------------------------------------------------------------
