@@ -104,3 +104,15 @@ def test_clock_log_parsing(tmp_path):
     out = s.stop()
     assert out["samples"] == 3 and out["sm_mhz"] == 1950.0 and out["sm_max_mhz"] == 1965.0
     assert out["reasons"] == ["hw_thermal_slowdown", "sw_power_cap"]
+
+
+def test_committed_traffic_profile_belongs_to_this_kernel_build():
+    """bench.py reports `roofline.traffic` only from an ncu capture of THIS kernel build: profiles/r02_traffic.json is keyed by the
+    hash of the kernel sources.  A kernel edit without a new capture must be noticed (the line then says traffic: null)."""
+    import json
+    import bench
+    tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(bench.__file__)), "profiles", "r02_traffic.json")))
+    assert tj["kernel_source_sha"] == bench.kernel_source_sha(), "kernel sources changed after the last ncu capture: re-run tools/profile_r02.sh"
+    for cfg in ("cfg3", "cfg2"):
+        for k in ("k_extend_march", "k_shadow"):
+            assert tj[cfg][k]["dram_bytes_per_launch"] > 0

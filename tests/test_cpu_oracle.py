@@ -186,3 +186,50 @@ def test_film_postprocess_formulas(oracle):
     only = oracle.film_postprocess(L.POST_COLOR_ONLY, w, h, pl)
     neg = (pl["color"].reshape(h, w, 3)[::-1] < 0)
     assert (only[neg] == 255).all()
+
+
+def test_sphere_first_fold_equals_the_insertion_order_fold(oracle):
+    """The argument behind `fold_all` (rt_kernels.cuh, k_extend_march): for a [spheres] Mandelbox [spheres] scene, testing ALL
+    spheres first and marching the SDF last against the nearest sphere - accepting its t when it is smaller, or equal with the
+    sphere later in insertion order - gives the reference's insertion-order fold (hitable.rs:177-198) bit for bit.  Checked here
+    with the ORACLE's own closest-hit fold, its sphere-only fold and its sphere-march, on rays chosen so that every case of the
+    proof occurs: the SDF wins, an earlier sphere wins, a LATER sphere cuts the march short, nothing is hit."""
+    from rayn_b200.scene import HitableStore, World
+    cam, world = configs.setup((64, 64), volume=False, fractal="mandelbox")
+    desc, keep = world.flatten(cam)
+    items = world.hitables.items
+    hk = [i for i, h in enumerate(items) if hasattr(h, "sdf")][0]
+    assert 0 < hk < len(items) - 1, "the setup.rs scene has spheres on both sides of the Mandelbox"
+    spheres = HitableStore()
+    sphere_index = []  # index in the full scene of every sphere of the sphere-only scene
+    for i, h in enumerate(items):
+        if i != hk:
+            spheres.push(h)
+            sphere_index.append(i)
+    sphere_index = np.asarray(sphere_index)
+    world_s = World(spheres, world.lights, world.materials, world.cameras, world.volume_params, world.consts)
+    desc_s, keep_s = world_s.flatten(cam)
+    rng = np.random.default_rng(11)
+    o1, d1 = random_rays(6000, 3)                                   # from outside towards the fractal
+    o2 = rng.uniform(-1.6, 1.6, size=(6000, 3)).astype(np.float32)  # from inside the scene towards the emitters
+    emit = np.array([[1.2, 1.2, 1.2], [1.2, -1.2, 1.2], [-1.2, -1.2, 1.2], [-1.2, 1.2, 1.2], [0.0, 0.0, 0.0]])
+    tgt = emit[rng.integers(0, 5, 6000)] + rng.normal(scale=0.12, size=(6000, 3))
+    d2 = tgt - o2
+    d2 = (d2 / np.linalg.norm(d2, axis=1, keepdims=True)).astype(np.float32)
+    o, d = np.concatenate([o1, o2]), np.concatenate([d1, d2])
+    for depth, thr_scale in ((1, 0.0001 * 2.0 * 1.0), (3, 0.0001 * 2.0 * 3.0)):  # film.rs:549 hit_threshold_at for depth > 0
+        t_ref, id_ref = oracle.kat_closest_hit(desc, depth, o, d)
+        c, ids = oracle.kat_closest_hit(desc_s, depth, o, d)         # fold over the spheres alone (same strict-min rule)
+        owner = np.where(ids >= 0, sphere_index[np.maximum(ids, 0)], -1)
+        t_sdf = oracle.kat_sdf_hit(desc.hitables[hk], desc.consts, o, d, c, np.float32(thr_scale), 0)
+        with np.errstate(invalid="ignore"):
+            take = (t_sdf < c) | ((t_sdf == c) & (owner > hk))
+        t_new = np.where(take, t_sdf, c).astype(np.float32)
+        id_new = np.where(take, hk, owner)
+        assert_bit_equal(t_new, t_ref, f"sphere-first fold t, depth {depth}")
+        assert (id_new == id_ref).all()
+        later = (id_ref > hk).sum()
+        assert (id_ref == hk).sum() > 500 and later > 200 and (id_ref == 0).sum() > 200, "every case of the proof must occur"
+        # the interesting case: a later sphere ends the march before the SDF's own stop
+        t_full = oracle.kat_sdf_hit(desc.hitables[hk], desc.consts, o, d, np.full(len(o), 200.0, np.float32), np.float32(thr_scale), 0)
+        assert ((t_full != t_sdf) & (id_ref > hk)).sum() > 50
